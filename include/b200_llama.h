@@ -1,0 +1,85 @@
+/* b200_llama.h -- C ABI of the B200-native replacement for llama.swift's decode hot path.
+ *
+ * This is the drop-in boundary: the two C++ functions that -[LlamaPredictOperation main]
+ * (Sources/llamaObjCxx/bridge/LlamaPredictOperation.mm, "PO.mm") calls -- llama_model_load (PO.mm:98) and
+ * llama_eval (PO.mm:510-518) -- plus the bits of llama_model / gpt_vocab the token loop reads
+ * (hparams.n_ctx PO.mm:812, hparams.n_vocab PO.mm:858, vocab.id_to_token PO.mm:893) and ggml_free (PO.mm:900).
+ * Plain pointers and sizes only; no exceptions cross the boundary.  INTEGRATION.md shows the Obj-C++ binding.
+ *
+ * Error convention (headers/LlamaError.h:14-19): 0 on success, otherwise the reference's LlamaErrorCode
+ * (-1000 failed to load model, -1001 prediction failed) with a message in `err`.
+ */
+#ifndef B200_LLAMA_H
+#define B200_LLAMA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_LLAMA_OK 0
+#define B200_LLAMA_ERR_LOAD (-1000)    /* LlamaErrorCodeFailedToLoadModel, headers/LlamaError.h:17 */
+#define B200_LLAMA_ERR_PREDICT (-1001) /* LlamaErrorCodePredictionFailed,  headers/LlamaError.h:18 */
+
+typedef struct b200_llama b200_llama;
+
+/* == llama_model_load(fname, model, vocab, n_ctx, &err), PO.mm:98-498.
+ * Reads the "ggml"-magic file (and its .1 .. .n-1 part files, PO.mm:312-322), merges column/row splits
+ * (PO.mm:358-388), re-lays the Q4 blocks out for the GPU and allocates the f32 KV cache (PO.mm:290-304) in HBM.
+ * device: CUDA device ordinal to place the model on. */
+int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen);
+
+/* == llama_eval(model, n_threads, n_past, embd_inp, embd_w, mem_per_token, &err), PO.mm:510-735.
+ * Evaluates n_tokens tokens at positions [n_past, n_past + n_tokens), appending their K/V rows, and writes the
+ * LAST token's logits (n_vocab floats, PO.mm:724-725) to host memory `logits_out`.  May be called again with a
+ * smaller n_past (the probe call at PO.mm:822 is later overwritten).  n_threads is the reference's thread count:
+ * no host threads are used here, but the value selects the reference's thread-partitioned summation order of the
+ * V*softmax(KQ) product (ggml.c:5553-5577, 5619-5665) so results match the reference run with that many threads. */
+int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens,
+                    float *logits_out, char *err, size_t errlen);
+
+/* == ggml_free(model.ctx), PO.mm:900 */
+void b200_llama_free(b200_llama *m);
+
+/* llama_hparams fields the caller reads (PO.mm:41-50) */
+int b200_llama_n_vocab(const b200_llama *m);
+int b200_llama_n_ctx(const b200_llama *m);
+int b200_llama_n_embd(const b200_llama *m);
+int b200_llama_n_layer(const b200_llama *m);
+int b200_llama_n_head(const b200_llama *m);
+int b200_llama_ftype(const b200_llama *m);
+
+/* gpt_vocab::id_to_token (utils.h:49-55; used at PO.mm:893).  Returns a pointer owned by the model; *len = bytes. */
+const char *b200_llama_token_str(const b200_llama *m, int id, int *len);
+
+/* Device-resident decode loop (no reference equivalent; used by bench.py's `value` leg and by teacher-forced
+ * parity runs).  Starting with `first_token` at position n_past, runs n_steps single-token evaluations entirely on
+ * the GPU: after each step the next input token is forced_tokens[i] if forced_tokens != NULL, else the arg-max of
+ * the logits (greedy).  tokens_out[i] receives the arg-max of step i.  If logits_all != NULL it receives
+ * n_steps * n_vocab floats.  *elapsed_ms (optional) = CUDA-event time of the loop on the model's stream. */
+int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first_token, int n_steps,
+                             const int32_t *forced_tokens, int32_t *tokens_out, float *logits_all,
+                             float *elapsed_ms, char *err, size_t errlen);
+
+/* Test-only: KV cache rows [0, n_rows) of one layer in the reference layout [n_ctx][n_embd] f32, K already roped
+ * (PO.mm:300-301, 586-587, 604-611).  which: 0 = K, 1 = V. */
+int b200_llama_kv_export(const b200_llama *m, int layer, int which, int n_rows, float *out);
+int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const float *in);
+
+/* Introspection for bench.py / profiles: number of kernel launches issued by the last eval/decode call, bytes of
+ * quantized weights resident, and a knob to toggle CUDA-graph replay + programmatic dependent launch. */
+long long b200_llama_last_launches(const b200_llama *m);
+long long b200_llama_weight_bytes(const b200_llama *m);
+int b200_llama_set_option(b200_llama *m, const char *key, int value);
+
+/* Stand-alone kernels behind the same ABI, for kernel-level parity tests (level 1):
+ * out[M] = W[M x K] (Q4_0, ggml row layout) * x[K] computed exactly as ggml_compute_forward_mul_mat_q4_0_f32 does. */
+int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out,
+                     int lane_pairs, float *kernel_ms, char *err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LLAMA_H */

@@ -1,0 +1,180 @@
+"""llama.swift_b200 -- B200-native (sm_100a) replacement for llama.swift's ggml Q4_0 decode hot path.
+
+Python host-side mirror of the reference's driver interface (bridge/LlamaPredictOperation.mm): the same two entry
+points with the same argument meaning and error behaviour --
+
+    llama_model_load(fname, n_ctx)                      PO.mm:98    -> LlamaModel
+    llama_eval(model, n_threads, n_past, embd_inp)      PO.mm:510   -> logits of the last token
+
+-- implemented by calling the C ABI of libb200llama.so (include/b200_llama.h) through ctypes.  There is no CPU
+path: if the CUDA library is missing or no GPU is present the calls raise.  (The directory name contains a dot, so
+import it through the repo-root shim:  `import llama_swift_b200`.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ggml_format  # noqa: F401  (writer for the reference's model file format)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200llama.so")
+
+ERR_LOAD = -1000      # LlamaErrorCodeFailedToLoadModel, headers/LlamaError.h:17
+ERR_PREDICT = -1001   # LlamaErrorCodePredictionFailed,  headers/LlamaError.h:18
+
+
+class LlamaError(RuntimeError):
+    """Mirror of NSError(domain com.alexrozanski.llama.error, code) raised by the bridge (PO.mm:90-95)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library.  Fails loudly when it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python llama.swift_b200/build.py` "
+                          "(nvcc, sm_100a).  llama.swift_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cp, sz = C.c_void_p, C.c_int, C.c_char_p, C.c_size_t
+    L.b200_llama_load.argtypes = [cp, ci, ci, C.POINTER(vp), cp, sz]
+    L.b200_llama_load.restype = ci
+    L.b200_llama_eval.argtypes = [vp, ci, ci, vp, ci, vp, cp, sz]
+    L.b200_llama_eval.restype = ci
+    L.b200_llama_free.argtypes = [vp]
+    L.b200_llama_free.restype = None
+    for n in ("n_vocab", "n_ctx", "n_embd", "n_layer", "n_head", "ftype"):
+        f = getattr(L, "b200_llama_" + n)
+        f.argtypes, f.restype = [vp], ci
+    L.b200_llama_token_str.argtypes = [vp, ci, C.POINTER(ci)]
+    L.b200_llama_token_str.restype = C.POINTER(C.c_char)
+    L.b200_llama_decode_device.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, C.POINTER(C.c_float), cp, sz]
+    L.b200_llama_decode_device.restype = ci
+    L.b200_llama_kv_export.argtypes = [vp, ci, ci, ci, vp]
+    L.b200_llama_kv_export.restype = ci
+    L.b200_llama_kv_import.argtypes = [vp, ci, ci, ci, vp]
+    L.b200_llama_kv_import.restype = ci
+    L.b200_llama_last_launches.argtypes, L.b200_llama_last_launches.restype = [vp], C.c_longlong
+    L.b200_llama_weight_bytes.argtypes, L.b200_llama_weight_bytes.restype = [vp], C.c_longlong
+    L.b200_llama_set_option.argtypes, L.b200_llama_set_option.restype = [vp, cp, ci], ci
+    L.b200_q4_0_matvec.argtypes = [ci, vp, ci, ci, vp, vp, ci, C.POINTER(C.c_float), cp, sz]
+    L.b200_q4_0_matvec.restype = ci
+    _lib = L
+    return L
+
+
+class LlamaModel:
+    """llama_model + gpt_vocab as the token loop sees them (PO.mm:71-88, utils.h:49-55)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        L = lib()
+        self.n_vocab = L.b200_llama_n_vocab(self._h)
+        self.n_ctx = L.b200_llama_n_ctx(self._h)
+        self.n_embd = L.b200_llama_n_embd(self._h)
+        self.n_layer = L.b200_llama_n_layer(self._h)
+        self.n_head = L.b200_llama_n_head(self._h)
+        self.ftype = L.b200_llama_ftype(self._h)
+
+    def free(self) -> None:            # ggml_free(model.ctx), PO.mm:900
+        if self._h:
+            lib().b200_llama_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def id_to_token(self, i: int) -> bytes:
+        n = C.c_int(0)
+        p = lib().b200_llama_token_str(self._h, i, C.byref(n))
+        return C.string_at(p, n.value)
+
+    def set_option(self, key: str, value: int) -> None:
+        if lib().b200_llama_set_option(self._h, key.encode(), value) != 0:
+            raise KeyError(key)
+
+    @property
+    def last_launches(self) -> int:
+        return int(lib().b200_llama_last_launches(self._h))
+
+    @property
+    def weight_bytes(self) -> int:
+        return int(lib().b200_llama_weight_bytes(self._h))
+
+    def kv_export(self, layer: int, which: int, n_rows: int) -> np.ndarray:
+        out = np.empty((n_rows, self.n_embd), dtype=np.float32)
+        if lib().b200_llama_kv_export(self._h, layer, which, n_rows, out.ctypes.data) != 0:
+            raise LlamaError(ERR_PREDICT, "kv_export failed")
+        return out
+
+    def kv_import(self, layer: int, which: int, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if lib().b200_llama_kv_import(self._h, layer, which, rows.shape[0], rows.ctypes.data) != 0:
+            raise LlamaError(ERR_PREDICT, "kv_import failed")
+
+    def decode_device(self, n_past: int, first_token: int, n_steps: int, n_threads: int = 8, forced_tokens=None,
+                      want_logits: bool = False):
+        """Device-resident greedy / teacher-forced loop.  Returns (argmax tokens, logits or None, elapsed ms)."""
+        toks = np.empty(n_steps, dtype=np.int32)
+        forced = None if forced_tokens is None else np.ascontiguousarray(forced_tokens, dtype=np.int32)
+        logits = np.empty((n_steps, self.n_vocab), dtype=np.float32) if want_logits else None
+        ms = C.c_float(0)
+        err = C.create_string_buffer(512)
+        rc = lib().b200_llama_decode_device(self._h, n_threads, n_past, int(first_token), n_steps,
+                                            None if forced is None else forced.ctypes.data, toks.ctypes.data,
+                                            None if logits is None else logits.ctypes.data, C.byref(ms), err, 512)
+        if rc != 0:
+            raise LlamaError(rc, err.value.decode(errors="replace"))
+        return toks, logits, ms.value
+
+
+def llama_model_load(fname: str, n_ctx: int = 512, device: int = 0) -> LlamaModel:
+    """llama_model_load(fname, model, vocab, n_ctx, &err), PO.mm:98.  The reference's caller passes 512 (PO.mm:790)."""
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_load(os.fsencode(fname), n_ctx, device, C.byref(h), err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return LlamaModel(h.value)
+
+
+def llama_eval(model: LlamaModel, n_threads: int, n_past: int, embd_inp) -> np.ndarray:
+    """llama_eval(model, n_threads, n_past, embd_inp, embd_w, mem_per_token, &err), PO.mm:510-518:
+    returns embd_w, the n_vocab logits of the LAST token of embd_inp (PO.mm:724-725)."""
+    toks = np.ascontiguousarray(embd_inp, dtype=np.int32)
+    logits = np.empty(model.n_vocab, dtype=np.float32)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_eval(model._h, n_threads, n_past, toks.ctypes.data, len(toks), logits.ctypes.data, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return logits
+
+
+def q4_0_matvec(w_blocks: np.ndarray, x: np.ndarray, lane_pairs: int = 0, device: int = 0, timed: bool = False):
+    """out[M] = W (Q4_0, ggml rows of 20-byte blocks) * x through the production mat-vec kernel."""
+    w = np.ascontiguousarray(w_blocks, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    K = x.shape[0]
+    M = w.size // (K // 32 * 20)
+    out = np.empty(M, dtype=np.float32)
+    ms = C.c_float(0)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_q4_0_matvec(device, w.ctypes.data, M, K, x.ctypes.data, out.ctypes.data, lane_pairs,
+                                C.byref(ms) if timed else None, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return (out, ms.value) if timed else out

@@ -1,0 +1,44 @@
+"""Build the product library llama.swift_b200/libb200llama.so IN-TREE with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.  No torch, no CPU fallback:
+csrc/engine.cu (kernels + C ABI, nvcc) and csrc/host_math.cpp (host libm constants, g++ via nvcc -x c++ passthrough).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libb200llama.so")
+SRCS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "host_math.cpp", "kernels.cuh", "ptx.cuh")]
+SRCS.append(os.path.join(HERE, "..", "include", "b200_llama.h"))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in SRCS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    obj_host = os.path.join(HERE, "csrc", "host_math.o")
+    # host constants: plain g++ semantics (no contraction, F16C for the fp16 conversions)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mf16c", "-c",
+                           os.path.join(HERE, "csrc", "host_math.cpp"), "-o", obj_host])
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+           "-fmad=false",                       # FMAs only where the reference has them (explicit fmaf / fma.rn.f32x2)
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "g++",
+           os.path.join(HERE, "csrc", "engine.cu"), obj_host, "-o", LIB, "-lcudart"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,749 @@
+// Host engine + C ABI (include/b200_llama.h) for the B200-native llama.swift decode path.
+//
+//   b200_llama_load  == llama_model_load  (PO.mm:98-498)   file -> HBM (tile-major Q4_0 streams, f32 KV cache)
+//   b200_llama_eval  == llama_eval        (PO.mm:510-735)  per-token kernel pipeline, replayed as a CUDA graph --
+//                       the replacement for ggml_graph_compute's pthread INIT/COMPUTE/FINALIZE scheduler
+//                       (ggml.c:9109-9555): 5 kernels per layer instead of 36 graph nodes, no host threads.
+//
+// There is deliberately no CPU fallback: every entry point fails with an error if CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_llama.h"
+#include "kernels.cuh"
+
+namespace b200 {
+void host_build_tables(uint16_t *table_silu_f16, uint16_t *table_exp_f16);
+void host_build_rope(double *cs, int n_ctx, int head_dim);
+float host_kq_scale(int n_embd, int n_head);
+}  // namespace b200
+
+using namespace b200;
+
+namespace {
+
+constexpr int kSmemBudget = 227 * 1024;
+
+void set_err(char *err, size_t errlen, const char *fmt, ...) {
+  if (!err || !errlen) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, errlen, fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      set_err(err, errlen, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #expr); \
+      return fail_code;                                                                                  \
+    }                                                                                                    \
+  } while (0)
+
+struct GemvPlan {
+  uint8_t *d_w = nullptr;
+  size_t bytes = 0;
+  int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
+  size_t smem = 0;
+};
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
+GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
+  GemvPlan p;
+  p.M = M;
+  p.nb = K / 32;
+  const int Mpad = (M + 3) & ~3;
+  p.g_total = Mpad / 4;
+  p.n_cta = std::min(n_sm, p.g_total);
+  p.rmax = 4 * ((p.g_total + p.n_cta - 1) / p.n_cta);
+  int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);
+  if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
+  while (p.rmax * (4 / lp) > 512 && lp < 4) lp *= 2;
+  p.lp = lp;
+  p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
+  const int chunk_target = env_int("B200_CHUNK_BYTES", 16384);
+  p.cb = std::max(1, std::min(p.nb, (chunk_target + p.rmax * 10) / (p.rmax * 20)));
+  p.stage_bytes = (p.cb * p.rmax * 20 + 127) & ~127;
+  const int nchunks = (p.nb + p.cb - 1) / p.cb;
+  const size_t fixed = (size_t) p.nb * 64 + (size_t) ((p.nb + 3) & ~3) * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+  int S = (int) ((kSmemBudget - fixed - 256) / (p.stage_bytes + 16));
+  S = std::max(1, std::min(S, nchunks));
+  p.S = S;
+  p.smem = (size_t) S * p.stage_bytes + fixed + (size_t) 2 * S * 8;
+  p.bytes = (size_t) p.g_total * 4 * p.nb * 20;
+  return p;
+}
+
+template <int LP, int PRO, int EPI>
+cudaError_t launch_gemv_t(const GemvPlan &p, const GemvArgs &a, cudaStream_t st, bool pdl) {
+  auto kern = q4_gemv_kernel<LP, PRO, EPI>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.n_cta);
+  cfg.blockDim = dim3(p.threads);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <int PRO, int EPI>
+cudaError_t launch_gemv_lp(const GemvPlan &p, const GemvArgs &a, cudaStream_t st, bool pdl) {
+  switch (p.lp) {
+    case 1: return launch_gemv_t<1, PRO, EPI>(p, a, st, pdl);
+    case 2: return launch_gemv_t<2, PRO, EPI>(p, a, st, pdl);
+    default: return launch_gemv_t<4, PRO, EPI>(p, a, st, pdl);
+  }
+}
+
+template <int PRO, int EPI>
+cudaError_t configure_gemv() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(q4_gemv_kernel<1, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_gemv_kernel<2, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(q4_gemv_kernel<4, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+}
+
+// opt every kernel instance on the current device in to 227 KB of dynamic shared memory
+cudaError_t configure_kernels() {
+  cudaError_t e;
+  if ((e = configure_gemv<PRO_NORM, EPI_QKV>()) != cudaSuccess) return e;
+  if ((e = configure_gemv<PRO_PLAIN, EPI_RESID>()) != cudaSuccess) return e;
+  if ((e = configure_gemv<PRO_NORM, EPI_SILU_MUL>()) != cudaSuccess) return e;
+  if ((e = configure_gemv<PRO_NORM, EPI_STORE>()) != cudaSuccess) return e;
+  if ((e = configure_gemv<PRO_PLAIN, EPI_STORE>()) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+}
+
+GemvArgs base_args(const GemvPlan &p) {
+  GemvArgs a = {};
+  a.w = p.d_w; a.M = p.M; a.g_total = p.g_total; a.nb = p.nb; a.cb = p.cb;
+  a.n_stages = p.S; a.stage_bytes = p.stage_bytes; a.rmax = p.rmax;
+  return a;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_small(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+struct HostTensor {
+  int n_dims = 0, ftype = 0;
+  int ne[2] = {1, 1};
+  std::vector<uint8_t> data;
+};
+
+}  // namespace
+
+struct b200_llama {
+  // llama_hparams, PO.mm:41-50
+  int n_vocab = 0, n_ctx = 0, n_embd = 0, n_mult = 0, n_head = 0, n_layer = 0, n_rot = 0, f16 = 0, n_ff = 0;
+  std::vector<std::string> id_to_token;
+
+  int device = 0, n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  struct Layer {
+    GemvPlan qkv, wo, w13, w2;
+    float *attn_norm = nullptr, *ffn_norm = nullptr;
+  };
+  std::vector<Layer> layers;
+  GemvPlan out;
+  float *d_norm = nullptr;
+  uint8_t *d_tok_emb = nullptr;     // raw ggml rows (get_rows needs one row per token)
+  float *d_k = nullptr, *d_v = nullptr;   // [n_layer][n_ctx][n_embd] f32, PO.mm:290-304
+  double2 *d_rope = nullptr;
+  uint16_t *d_silu = nullptr, *d_exp = nullptr;
+  float *d_inpL = nullptr, *d_inpFF = nullptr, *d_q = nullptr, *d_att = nullptr, *d_h = nullptr, *d_logits = nullptr;
+  StepParams *d_sp = nullptr;
+  int *d_token_log = nullptr, *d_forced = nullptr;
+  float *d_logits_log = nullptr;
+  size_t logits_log_cap = 0;
+  int log_cap = 0;
+  float *h_logits = nullptr;        // pinned
+  float kq_scale = 0.f;
+  long long weight_bytes = 0;
+  long long last_launches = 0;
+
+  int opt_graph = 1, opt_pdl = 0;
+  cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
+  int graph_threads = -1, graph_pdl = -1;
+};
+
+namespace {
+
+int attn_smem_bytes(const b200_llama *m, int n_threads) {
+  return (int) ((((size_t) m->n_ctx * 4 + 15) & ~(size_t) 15) + 8 * 8 + 8 * 4 + (size_t) n_threads * 32 * 4 + 64);
+}
+
+// One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
+cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *launches) {
+  cudaStream_t st = m->stream;
+  cudaError_t e;
+  const int E = m->n_embd;
+  long long n = 0;
+  e = launch_small(embed_kernel, dim3((E + 255) / 256), dim3(256), 0, st, pdl,
+                   (const uint8_t *) m->d_tok_emb, (const StepParams *) m->d_sp, m->d_inpL, E);
+  if (e != cudaSuccess) return e;
+  n++;
+  for (int il = 0; il < m->n_layer; il++) {
+    b200_llama::Layer &L = m->layers[il];
+    float *k_layer = m->d_k + (size_t) il * m->n_ctx * E;
+    float *v_layer = m->d_v + (size_t) il * m->n_ctx * E;
+    {  // norm * attention_norm -> wq|wk|wv -> rope -> Q buffer, KV cache      PO.mm:570-611
+      GemvArgs a = base_args(L.qkv);
+      a.x = m->d_inpL; a.norm_w = L.attn_norm; a.q_out = m->d_q; a.k_layer = k_layer; a.v_layer = v_layer;
+      a.rope = m->d_rope; a.sp = m->d_sp; a.n_embd = E; a.head_dim = E / m->n_head;
+      e = launch_gemv_lp<PRO_NORM, EPI_QKV>(L.qkv, a, st, pdl);
+      if (e != cudaSuccess) return e;
+      n++;
+    }
+    {  // KQ, scale, mask, soft_max, V*P, merge heads                             PO.mm:614-646
+      AttnArgs a = {};
+      a.q = m->d_q; a.k_layer = k_layer; a.v_layer = v_layer; a.out = m->d_att; a.sp = m->d_sp;
+      a.exp_table = m->d_exp; a.n_embd = E; a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.n_ctx = m->n_ctx;
+      e = launch_small(attn_kernel, dim3(m->n_head * ATTN_CLUSTER), dim3(ATTN_THREADS), attn_smem_bytes(m, n_threads), st, pdl, a);
+      if (e != cudaSuccess) return e;
+      n++;
+    }
+    {  // wo, + inpSA                                                              PO.mm:649-654
+      GemvArgs a = base_args(L.wo);
+      a.x = m->d_att; a.out = m->d_inpFF; a.resid = m->d_inpL;
+      e = launch_gemv_lp<PRO_PLAIN, EPI_RESID>(L.wo, a, st, pdl);
+      if (e != cudaSuccess) return e;
+      n++;
+    }
+    {  // norm * ffn_norm -> w1|w3 -> silu(w1 x) * (w3 x)                         PO.mm:660-680
+      GemvArgs a = base_args(L.w13);
+      a.x = m->d_inpFF; a.norm_w = L.ffn_norm; a.out = m->d_h; a.silu_table = m->d_silu;
+      e = launch_gemv_lp<PRO_NORM, EPI_SILU_MUL>(L.w13, a, st, pdl);
+      if (e != cudaSuccess) return e;
+      n++;
+    }
+    {  // w2, + inpFF                                                              PO.mm:682-687
+      GemvArgs a = base_args(L.w2);
+      a.x = m->d_h; a.out = m->d_inpL; a.resid = m->d_inpFF;
+      e = launch_gemv_lp<PRO_PLAIN, EPI_RESID>(L.w2, a, st, pdl);
+      if (e != cudaSuccess) return e;
+      n++;
+    }
+  }
+  {  // final norm * norm.weight -> output                                       PO.mm:694-706
+    GemvArgs a = base_args(m->out);
+    a.x = m->d_inpL; a.norm_w = m->d_norm; a.out = m->d_logits;
+    e = launch_gemv_lp<PRO_NORM, EPI_STORE>(m->out, a, st, pdl);
+    if (e != cudaSuccess) return e;
+    n++;
+  }
+  if (launches) *launches += n;
+  return cudaSuccess;
+}
+
+// Capture (once per {n_threads, pdl}) and replay the token step as a CUDA graph.
+cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
+  const bool pdl = m->opt_pdl != 0;
+  if (!m->opt_graph) return enqueue_token(m, n_threads, pdl, launches);
+  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != (int) pdl) {
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return e;
+    long long dummy = 0;
+    e = enqueue_token(m, n_threads, pdl, &dummy);
+    cudaError_t e2 = cudaStreamEndCapture(m->stream, &g);
+    if (e != cudaSuccess) { if (g) cudaGraphDestroy(g); return e; }
+    if (e2 != cudaSuccess) return e2;
+    e = cudaGraphInstantiate(&m->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return e;
+    m->graph_threads = n_threads;
+    m->graph_pdl = (int) pdl;
+  }
+  if (launches) *launches += 2 + 5LL * m->n_layer;
+  return cudaGraphLaunch(m->graph_exec, m->stream);
+}
+
+// Upload the concatenated raw rows of the fused matrices and repack them into the tile-major stream.
+cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<const HostTensor *> &parts, int interleave_half,
+                          uint8_t *d_stage) {
+  cudaError_t e = cudaMalloc(&p.d_w, p.bytes);
+  if (e != cudaSuccess) return e;
+  size_t off = 0;
+  for (const HostTensor *t : parts) {
+    e = cudaMemcpyAsync(d_stage + off, t->data.data(), t->data.size(), cudaMemcpyHostToDevice, m->stream);
+    if (e != cudaSuccess) return e;
+    off += t->data.size();
+  }
+  const long long total = (long long) p.g_total * 4 * p.nb;
+  const int threads = 256;
+  repack_q4_0_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
+      d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  m->weight_bytes += (long long) p.M * p.nb * 20;
+  return cudaStreamSynchronize(m->stream);
+}
+
+void free_model(b200_llama *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  for (auto &L : m->layers) {
+    cudaFree(L.qkv.d_w); cudaFree(L.wo.d_w); cudaFree(L.w13.d_w); cudaFree(L.w2.d_w);
+    cudaFree(L.attn_norm); cudaFree(L.ffn_norm);
+  }
+  cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
+  cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
+  cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h); cudaFree(m->d_logits);
+  cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
+  if (m->h_logits) cudaFreeHost(m->h_logits);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const std::map<int, int> kNParts = {{4096, 1}, {5120, 2}, {6656, 4}, {8192, 8}};   // LLAMA_N_PARTS, PO.mm:33-38
+
+}  // namespace
+
+extern "C" {
+
+int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_LOAD;
+  if (!out) { set_err(err, errlen, "null out pointer"); return fail_code; }
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    set_err(err, errlen, "no CUDA device available (this library has no CPU path)");
+    return fail_code;
+  }
+  if (device < 0 || device >= n_dev) { set_err(err, errlen, "bad device ordinal %d", device); return fail_code; }
+
+  std::ifstream fin(path, std::ios::binary);
+  if (!fin) { set_err(err, errlen, "failed to open '%s'", path); return fail_code; }                       // PO.mm:100-104
+  uint32_t magic = 0;
+  fin.read((char *) &magic, sizeof(magic));
+  if (magic != 0x67676d6c) { set_err(err, errlen, "invalid model file '%s' (bad magic)", path); return fail_code; }   // PO.mm:110-114
+
+  b200_llama *m = new b200_llama();
+  struct Guard { b200_llama *p; ~Guard() { if (p) free_model(p); } } guard{m};
+  m->device = device;
+  int32_t hp[7] = {0};
+  fin.read((char *) hp, sizeof(hp));                                                                        // PO.mm:124-131
+  m->n_vocab = hp[0]; m->n_embd = hp[1]; m->n_mult = hp[2]; m->n_head = hp[3]; m->n_layer = hp[4]; m->n_rot = hp[5]; m->f16 = hp[6];
+  m->n_ctx = n_ctx;
+  if (!fin || m->n_vocab <= 0 || m->n_embd <= 0 || m->n_mult <= 0 || m->n_head <= 0 || m->n_layer <= 0 || n_ctx <= 0) {
+    set_err(err, errlen, "invalid model file '%s' (bad header)", path);
+    return fail_code;
+  }
+  m->n_ff = ((2 * (4 * m->n_embd) / 3 + m->n_mult - 1) / m->n_mult) * m->n_mult;                             // PO.mm:135
+  auto np = kNParts.find(m->n_embd);
+  if (np == kNParts.end()) { set_err(err, errlen, "unsupported n_embd %d (LLAMA_N_PARTS has no entry)", m->n_embd); return fail_code; }   // PO.mm:136 throws
+  const int n_parts = np->second;
+  if (m->n_embd % m->n_head != 0 || m->n_embd / m->n_head != 128) {
+    set_err(err, errlen, "unsupported head size %d (kernels are built for 128)", m->n_embd / std::max(1, m->n_head));
+    return fail_code;
+  }
+  m->id_to_token.resize(m->n_vocab);
+  for (int i = 0; i < m->n_vocab; i++) {                                                                    // PO.mm:149-163
+    uint32_t len = 0;
+    fin.read((char *) &len, sizeof(len));
+    if (!fin || len > (1u << 20)) { set_err(err, errlen, "invalid model file '%s' (bad vocab)", path); return fail_code; }
+    m->id_to_token[i].resize(len);
+    fin.read(&m->id_to_token[i][0], len);
+  }
+  switch (m->f16) {                                                                                         // PO.mm:169-180
+    case 2: break;
+    case 0: case 1: case 3:
+      set_err(err, errlen, "model file '%s' has weight type %d; this build accelerates Q4_0 (type 2) only", path, m->f16);
+      return fail_code;
+    default:
+      set_err(err, errlen, "invalid model file '%s' (bad f16 value %d)", path, m->f16);
+      return fail_code;
+  }
+  const size_t file_offset = (size_t) fin.tellg();
+  fin.close();
+
+  // expected tensors, PO.mm:246-286
+  const int E = m->n_embd, F = m->n_ff, V = m->n_vocab;
+  std::map<std::string, HostTensor> tensors;
+  auto expect = [&](const std::string &name, int ne0, int ne1, int n_dims) {
+    HostTensor t; t.n_dims = n_dims; t.ne[0] = ne0; t.ne[1] = ne1;
+    t.data.resize(n_dims == 1 ? (size_t) ne0 * 4 : (size_t) ne1 * (ne0 / 32) * 20);
+    tensors[name] = std::move(t);
+  };
+  expect("tok_embeddings.weight", E, V, 2);
+  expect("norm.weight", E, 1, 1);
+  expect("output.weight", E, V, 2);
+  for (int i = 0; i < m->n_layer; i++) {
+    const std::string p = "layers." + std::to_string(i) + ".";
+    expect(p + "attention_norm.weight", E, 1, 1);
+    expect(p + "attention.wq.weight", E, E, 2);
+    expect(p + "attention.wk.weight", E, E, 2);
+    expect(p + "attention.wv.weight", E, E, 2);
+    expect(p + "attention.wo.weight", E, E, 2);
+    expect(p + "ffn_norm.weight", E, 1, 1);
+    expect(p + "feed_forward.w1.weight", E, F, 2);
+    expect(p + "feed_forward.w2.weight", F, E, 2);
+    expect(p + "feed_forward.w3.weight", E, F, 2);
+  }
+  std::map<std::string, int> seen;
+
+  for (int part = 0; part < n_parts; part++) {                                                              // PO.mm:312-495
+    std::string fname = path;
+    if (part > 0) fname += "." + std::to_string(part);
+    std::ifstream fp(fname, std::ios::binary);
+    if (!fp) { set_err(err, errlen, "failed to open '%s'", fname.c_str()); return fail_code; }
+    fp.seekg(file_offset);
+    while (true) {
+      int32_t n_dims = 0, length = 0, ftype = 0;
+      fp.read((char *) &n_dims, 4); fp.read((char *) &length, 4); fp.read((char *) &ftype, 4);
+      if (fp.eof()) break;
+      if (!fp || n_dims < 1 || n_dims > 2 || length <= 0 || length > 255) {
+        set_err(err, errlen, "corrupt tensor record in '%s'", fname.c_str());
+        return fail_code;
+      }
+      int32_t ne[2] = {1, 1};
+      int64_t nelements = 1;
+      for (int i = 0; i < n_dims; i++) { fp.read((char *) &ne[i], 4); nelements *= ne[i]; }
+      std::string name(length, 0);
+      fp.read(&name[0], length);
+      auto it = tensors.find(name);
+      if (it == tensors.end()) { set_err(err, errlen, "unknown tensor '%s' in model file", name.c_str()); return fail_code; }   // PO.mm:352-356
+      HostTensor &t = it->second;
+      int split_type = 0;                                                                                   // PO.mm:358-388
+      if (name.find("tok_embeddings") != std::string::npos) split_type = 0;
+      else if (name.find("layers") != std::string::npos) {
+        if (name.find("attention.wo.weight") != std::string::npos) split_type = 0;
+        else if (name.find("feed_forward.w2.weight") != std::string::npos) split_type = 0;
+        else split_type = 1;
+      } else if (name.find("output") != std::string::npos) split_type = 1;
+
+      if (n_dims == 1) {
+        if (t.n_dims != 1 || (int64_t) t.ne[0] != nelements) { set_err(err, errlen, "tensor '%s' has wrong size in model file", name.c_str()); return fail_code; }
+        if (ftype != 0) { set_err(err, errlen, "tensor '%s': 1-D tensors must be f32 (ftype %d)", name.c_str(), ftype); return fail_code; }
+        if (part == 0) fp.read((char *) t.data.data(), t.data.size());                                      // PO.mm:453-457
+        else fp.seekg(t.data.size(), std::ios::cur);
+      } else {
+        if (t.n_dims != 2 || (int64_t) t.ne[0] * t.ne[1] / n_parts != nelements) { set_err(err, errlen, "tensor '%s' has wrong size in model file", name.c_str()); return fail_code; }
+        const bool ok = split_type == 0 ? (t.ne[0] / n_parts == ne[0] && t.ne[1] == ne[1]) : (t.ne[0] == ne[0] && t.ne[1] / n_parts == ne[1]);
+        if (!ok) {
+          set_err(err, errlen, "tensor '%s' has wrong shape in model file: got [%d, %d], expected [%d, %d]", name.c_str(),
+                  split_type == 0 ? t.ne[0] / n_parts : t.ne[0], split_type == 0 ? t.ne[1] : t.ne[1] / n_parts, ne[0], ne[1]);
+          return fail_code;
+        }
+        if (ftype != 2) { set_err(err, errlen, "tensor '%s': ftype %d in a Q4_0 model file", name.c_str(), ftype); return fail_code; }
+        if (ne[0] % 64 != 0) { set_err(err, errlen, "tensor '%s': row length %d is not a multiple of 64", name.c_str(), ne[0]); return fail_code; }   // PO.mm:437
+        const size_t row_size = (size_t) t.ne[0] / 32 * 20;
+        if (n_parts == 1) {
+          fp.read((char *) t.data.data(), t.data.size());
+        } else if (split_type == 0) {                                                                       // PO.mm:467-477
+          for (int i1 = 0; i1 < ne[1]; ++i1) {
+            const size_t offset = (size_t) i1 * row_size + ((size_t) part * ne[0] / 32) * 20;
+            fp.read((char *) t.data.data() + offset, row_size / n_parts);
+          }
+        } else {                                                                                            // PO.mm:478-487
+          for (int i1 = 0; i1 < ne[1]; ++i1) {
+            const size_t offset_row = ((size_t) i1 + (size_t) part * ne[1]) * row_size;
+            fp.read((char *) t.data.data() + offset_row, row_size);
+          }
+        }
+      }
+      if (!fp) { set_err(err, errlen, "unexpected end of file in '%s' (tensor '%s')", fname.c_str(), name.c_str()); return fail_code; }
+      seen[name]++;
+    }
+  }
+  for (auto &kv : tensors) {
+    if (seen[kv.first] != n_parts) { set_err(err, errlen, "tensor '%s' missing from model file", kv.first.c_str()); return fail_code; }
+  }
+
+  // ---- device side ----
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_err(err, errlen, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return fail_code; }
+  m->n_sm = env_int("B200_NUM_CTAS", prop.multiProcessorCount);
+  CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&m->ev0));
+  CUDA_TRY(cudaEventCreate(&m->ev1));
+
+  const size_t stage_cap = std::max({(size_t) 3 * E * (E / 32) * 20, (size_t) 2 * F * (E / 32) * 20, (size_t) V * (E / 32) * 20});
+  uint8_t *d_stage = nullptr;
+  CUDA_TRY(cudaMalloc(&d_stage, stage_cap));
+  struct StageGuard { uint8_t *p; ~StageGuard() { cudaFree(p); } } sguard{d_stage};
+
+  auto upload_f32 = [&](const HostTensor &t, float **dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, t.data.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, t.data.data(), t.data.size(), cudaMemcpyHostToDevice);
+  };
+  const int lp_small = env_int("B200_LP_SMALL", 0), lp_qkv = env_int("B200_LP_QKV", 0), lp_w13 = env_int("B200_LP_W13", 0), lp_out = env_int("B200_LP_OUT", 0);
+  m->layers.resize(m->n_layer);
+  for (int i = 0; i < m->n_layer; i++) {
+    const std::string p = "layers." + std::to_string(i) + ".";
+    b200_llama::Layer &L = m->layers[i];
+    L.qkv = make_plan(3 * E, E, m->n_sm, lp_qkv);
+    CUDA_TRY(upload_matrix(m, L.qkv, {&tensors[p + "attention.wq.weight"], &tensors[p + "attention.wk.weight"], &tensors[p + "attention.wv.weight"]}, 0, d_stage));
+    L.wo = make_plan(E, E, m->n_sm, lp_small);
+    CUDA_TRY(upload_matrix(m, L.wo, {&tensors[p + "attention.wo.weight"]}, 0, d_stage));
+    L.w13 = make_plan(2 * F, E, m->n_sm, lp_w13);
+    CUDA_TRY(upload_matrix(m, L.w13, {&tensors[p + "feed_forward.w1.weight"], &tensors[p + "feed_forward.w3.weight"]}, F, d_stage));
+    L.w2 = make_plan(E, F, m->n_sm, lp_small);
+    CUDA_TRY(upload_matrix(m, L.w2, {&tensors[p + "feed_forward.w2.weight"]}, 0, d_stage));
+    CUDA_TRY(upload_f32(tensors[p + "attention_norm.weight"], &L.attn_norm));
+    CUDA_TRY(upload_f32(tensors[p + "ffn_norm.weight"], &L.ffn_norm));
+  }
+  m->out = make_plan(V, E, m->n_sm, lp_out);
+  CUDA_TRY(upload_matrix(m, m->out, {&tensors["output.weight"]}, 0, d_stage));
+  CUDA_TRY(upload_f32(tensors["norm.weight"], &m->d_norm));
+  {
+    const HostTensor &t = tensors["tok_embeddings.weight"];
+    CUDA_TRY(cudaMalloc(&m->d_tok_emb, t.data.size()));
+    CUDA_TRY(cudaMemcpy(m->d_tok_emb, t.data.data(), t.data.size(), cudaMemcpyHostToDevice));
+  }
+  tensors.clear();
+
+  const size_t kv_bytes = (size_t) m->n_layer * n_ctx * E * sizeof(float);                                  // PO.mm:297-301
+  CUDA_TRY(cudaMalloc(&m->d_k, kv_bytes));
+  CUDA_TRY(cudaMalloc(&m->d_v, kv_bytes));
+  CUDA_TRY(cudaMemset(m->d_k, 0, kv_bytes));
+  CUDA_TRY(cudaMemset(m->d_v, 0, kv_bytes));
+
+  {
+    std::vector<uint16_t> ts(1 << 16), te(1 << 16);
+    host_build_tables(ts.data(), te.data());
+    CUDA_TRY(cudaMalloc(&m->d_silu, ts.size() * 2));
+    CUDA_TRY(cudaMalloc(&m->d_exp, te.size() * 2));
+    CUDA_TRY(cudaMemcpy(m->d_silu, ts.data(), ts.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_exp, te.data(), te.size() * 2, cudaMemcpyHostToDevice));
+    const int hd = E / m->n_head;
+    std::vector<double> cs((size_t) n_ctx * hd);
+    host_build_rope(cs.data(), n_ctx, hd);
+    CUDA_TRY(cudaMalloc(&m->d_rope, cs.size() * 8));
+    CUDA_TRY(cudaMemcpy(m->d_rope, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice));
+    m->kq_scale = host_kq_scale(E, m->n_head);
+  }
+  CUDA_TRY(cudaMalloc(&m->d_inpL, E * 4));
+  CUDA_TRY(cudaMalloc(&m->d_inpFF, E * 4));
+  CUDA_TRY(cudaMalloc(&m->d_q, E * 4));
+  CUDA_TRY(cudaMalloc(&m->d_att, E * 4));
+  CUDA_TRY(cudaMalloc(&m->d_h, (size_t) F * 4));
+  CUDA_TRY(cudaMalloc(&m->d_logits, (size_t) V * 4));
+  CUDA_TRY(cudaMalloc(&m->d_sp, sizeof(StepParams)));
+  CUDA_TRY(cudaMemset(m->d_sp, 0, sizeof(StepParams)));
+  CUDA_TRY(cudaMallocHost(&m->h_logits, (size_t) V * 4));
+  CUDA_TRY(configure_kernels());
+  m->opt_graph = env_int("B200_GRAPH", 1);
+  m->opt_pdl = env_int("B200_PDL", 0);
+
+  *out = m;
+  guard.p = nullptr;
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits_out,
+                    char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  if (!m || !tokens || !logits_out) { set_err(err, errlen, "null argument"); return fail_code; }
+  if (n_tokens < 1 || n_past < 0 || n_past + n_tokens > m->n_ctx) {
+    set_err(err, errlen, "n_past %d + n_tokens %d exceeds n_ctx %d", n_past, n_tokens, m->n_ctx);
+    return fail_code;
+  }
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) { set_err(err, errlen, "n_threads %d > 64 not supported", n_threads); return fail_code; }
+  for (int i = 0; i < n_tokens; i++) {
+    if (tokens[i] < 0 || tokens[i] >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", tokens[i]); return fail_code; }
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  // The reference evaluates the N columns of every mat-mul independently, so the batch is run one token at a time;
+  // p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P partition, ggml.c:5628).
+  for (int i = 0; i < n_tokens; i++) {
+    set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, tokens[i], n_past + i, n_past + n_tokens, 0);
+    CUDA_TRY(cudaGetLastError());
+    m->last_launches++;
+    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first_token, int n_steps,
+                             const int32_t *forced_tokens, int32_t *tokens_out, float *logits_all, float *elapsed_ms,
+                             char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  if (!m) { set_err(err, errlen, "null model"); return fail_code; }
+  if (n_steps < 1 || n_past < 0 || n_past + n_steps > m->n_ctx) {
+    set_err(err, errlen, "n_past %d + n_steps %d exceeds n_ctx %d", n_past, n_steps, m->n_ctx);
+    return fail_code;
+  }
+  if (first_token < 0 || first_token >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", first_token); return fail_code; }
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) { set_err(err, errlen, "n_threads %d > 64 not supported", n_threads); return fail_code; }
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (m->log_cap < n_steps) {
+    cudaFree(m->d_token_log); cudaFree(m->d_forced);
+    m->d_token_log = nullptr; m->d_forced = nullptr;
+    CUDA_TRY(cudaMalloc(&m->d_token_log, (size_t) n_steps * 4));
+    CUDA_TRY(cudaMalloc(&m->d_forced, (size_t) n_steps * 4));
+    m->log_cap = n_steps;
+  }
+  if (forced_tokens) {
+    for (int i = 0; i < n_steps; i++)
+      if (forced_tokens[i] < 0 || forced_tokens[i] >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", forced_tokens[i]); return fail_code; }
+    CUDA_TRY(cudaMemcpyAsync(m->d_forced, forced_tokens, (size_t) n_steps * 4, cudaMemcpyHostToDevice, m->stream));
+  }
+  if (logits_all) {
+    const size_t need = (size_t) n_steps * m->n_vocab;
+    if (m->logits_log_cap < need) {
+      cudaFree(m->d_logits_log); m->d_logits_log = nullptr;
+      CUDA_TRY(cudaMalloc(&m->d_logits_log, need * 4));
+      m->logits_log_cap = need;
+    }
+  }
+  m->last_launches = 0;
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  for (int i = 0; i < n_steps; i++) {
+    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+    if (logits_all) {
+      CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced_tokens ? m->d_forced : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    m->last_launches++;
+  }
+  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, m->ev0, m->ev1));
+  if (tokens_out) CUDA_TRY(cudaMemcpy(tokens_out, m->d_token_log, (size_t) n_steps * 4, cudaMemcpyDeviceToHost));
+  if (logits_all) CUDA_TRY(cudaMemcpy(logits_all, m->d_logits_log, (size_t) n_steps * m->n_vocab * 4, cudaMemcpyDeviceToHost));
+  return B200_LLAMA_OK;
+}
+
+void b200_llama_free(b200_llama *m) { free_model(m); }
+
+int b200_llama_n_vocab(const b200_llama *m) { return m->n_vocab; }
+int b200_llama_n_ctx(const b200_llama *m) { return m->n_ctx; }
+int b200_llama_n_embd(const b200_llama *m) { return m->n_embd; }
+int b200_llama_n_layer(const b200_llama *m) { return m->n_layer; }
+int b200_llama_n_head(const b200_llama *m) { return m->n_head; }
+int b200_llama_ftype(const b200_llama *m) { return m->f16; }
+
+const char *b200_llama_token_str(const b200_llama *m, int id, int *len) {
+  if (id < 0 || id >= m->n_vocab) { if (len) *len = 0; return ""; }
+  if (len) *len = (int) m->id_to_token[id].size();
+  return m->id_to_token[id].data();
+}
+
+int b200_llama_kv_export(const b200_llama *m, int layer, int which, int n_rows, float *out) {
+  if (!m || layer < 0 || layer >= m->n_layer || n_rows < 0 || n_rows > m->n_ctx) return B200_LLAMA_ERR_PREDICT;
+  cudaSetDevice(m->device);
+  const float *base = (which == 0 ? m->d_k : m->d_v) + (size_t) layer * m->n_ctx * m->n_embd;
+  cudaStreamSynchronize(m->stream);
+  return cudaMemcpy(out, base, (size_t) n_rows * m->n_embd * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200_LLAMA_ERR_PREDICT;
+}
+
+int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const float *in) {
+  if (!m || layer < 0 || layer >= m->n_layer || n_rows < 0 || n_rows > m->n_ctx) return B200_LLAMA_ERR_PREDICT;
+  cudaSetDevice(m->device);
+  float *base = (which == 0 ? m->d_k : m->d_v) + (size_t) layer * m->n_ctx * m->n_embd;
+  cudaStreamSynchronize(m->stream);
+  return cudaMemcpy(base, in, (size_t) n_rows * m->n_embd * 4, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : B200_LLAMA_ERR_PREDICT;
+}
+
+long long b200_llama_last_launches(const b200_llama *m) { return m->last_launches; }
+long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes; }
+
+int b200_llama_set_option(b200_llama *m, const char *key, int value) {
+  if (!m || !key) return -1;
+  if (!strcmp(key, "graph")) { m->opt_graph = value; return 0; }
+  if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
+  return -1;
+}
+
+int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, int lane_pairs,
+                     float *kernel_ms, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { set_err(err, errlen, "no CUDA device available (this library has no CPU path)"); return fail_code; }
+  if (M < 1 || K < 64 || K % 64 != 0) { set_err(err, errlen, "bad shape %d x %d", M, K); return fail_code; }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  b200_llama tmp;   // only stream / counters are used by upload_matrix
+  tmp.device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+  GemvPlan p = make_plan(M, K, env_int("B200_NUM_CTAS", prop.multiProcessorCount), lane_pairs);
+  HostTensor t;
+  t.data.assign((const uint8_t *) w_ggml, (const uint8_t *) w_ggml + (size_t) M * (K / 32) * 20);
+  uint8_t *d_stage = nullptr;
+  float *d_x = nullptr, *d_out = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = B200_LLAMA_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_stage); cudaFree(d_x); cudaFree(d_out); cudaFree(p.d_w);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaStreamDestroy(tmp.stream);
+  };
+#define MV_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e__), #expr); cleanup(); return fail_code; } } while (0)
+  MV_TRY(configure_kernels());
+  MV_TRY(cudaMalloc(&d_stage, t.data.size()));
+  MV_TRY(upload_matrix(&tmp, p, {&t}, 0, d_stage));
+  MV_TRY(cudaMalloc(&d_x, (size_t) K * 4));
+  MV_TRY(cudaMalloc(&d_out, (size_t) M * 4));
+  MV_TRY(cudaMemcpy(d_x, x, (size_t) K * 4, cudaMemcpyHostToDevice));
+  MV_TRY(cudaEventCreate(&e0));
+  MV_TRY(cudaEventCreate(&e1));
+  GemvArgs a = base_args(p);
+  a.x = d_x; a.out = d_out;
+  const int reps = kernel_ms ? 5 : 1;
+  float best = 1e30f;
+  for (int i = 0; i < reps; i++) {
+    MV_TRY(cudaEventRecord(e0, tmp.stream));
+    MV_TRY((launch_gemv_lp<PRO_PLAIN, EPI_STORE>(p, a, tmp.stream, false)));
+    MV_TRY(cudaEventRecord(e1, tmp.stream));
+    MV_TRY(cudaStreamSynchronize(tmp.stream));
+    float ms = 0;
+    MV_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  if (kernel_ms) *kernel_ms = best;
+  MV_TRY(cudaMemcpy(out, d_out, (size_t) M * 4, cudaMemcpyDeviceToHost));
+#undef MV_TRY
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -13,7 +13,9 @@ b200_llama_load in this repository.
 """
 from __future__ import annotations
 
+import os
 import struct
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -42,6 +44,15 @@ class HParams:
         return ((2 * (4 * self.n_embd) // 3 + self.n_mult - 1) // self.n_mult) * self.n_mult
 
 
+def _round_half_away_f32(v: np.ndarray) -> np.ndarray:
+    """C round() on f32 data without going through f64: trunc, then step away from zero when |frac| >= 0.5.
+    (v - trunc(v) is exact in f32, so this has no double-rounding problem, unlike floor(|v| + 0.5) in f32.)"""
+    t = np.trunc(v)
+    frac = v - t
+    t += np.where(np.abs(frac) >= np.float32(0.5), np.sign(v), np.float32(0.0)).astype(np.float32)
+    return t
+
+
 def quantize_q4_0(w: np.ndarray) -> np.ndarray:
     """utils.cpp:431-486.  w: [rows, k] f32 -> uint8 [rows, k/32, 20] (f32 d, 16 nibble bytes)."""
     rows, k = w.shape
@@ -51,13 +62,12 @@ def quantize_q4_0(w: np.ndarray) -> np.ndarray:
     d = (amax / np.float32(7.0)).astype(np.float32)
     with np.errstate(divide="ignore"):
         idv = np.where(d != 0, np.float32(1.0) / d, np.float32(0.0)).astype(np.float32)
-    v = (x * idv[:, :, None]).astype(np.float32).astype(np.float64)
-    r = np.sign(v) * np.floor(np.abs(v) + 0.5)          # C round(): half away from zero
-    q = (r.astype(np.int8) + 8).astype(np.uint8)
-    packed = (q[:, :, 0::2] | (q[:, :, 1::2] << 4)).astype(np.uint8)
+    v = x * idv[:, :, None]
+    r = _round_half_away_f32(v)                          # C round(): half away from zero
+    q = (r.astype(np.int8) + np.int8(8)).view(np.uint8)
     out = np.empty((rows, k // QK, 20), dtype=np.uint8)
     out[:, :, :4] = d.view(np.uint8).reshape(rows, k // QK, 4)
-    out[:, :, 4:] = packed
+    np.bitwise_or(q[:, :, 0::2], q[:, :, 1::2] << 4, out=out[:, :, 4:])
     return out
 
 
@@ -71,11 +81,11 @@ def quantize_q4_1(w: np.ndarray) -> np.ndarray:
     # quirk kept: max starts at numeric_limits<float>::min() (smallest positive normal), utils.cpp:509
     mx = np.maximum(np.max(x, axis=2), np.finfo(np.float32).tiny).astype(np.float32)
     d = ((mx - mn).astype(np.float32) / np.float32(15.0)).astype(np.float32)
-    with np.errstate(divide="ignore"):
+    with np.errstate(all="ignore"):
         idv = np.where(d != 0, np.float32(1.0) / d, np.float32(0.0)).astype(np.float32)
-    v = ((x - mn[:, :, None]).astype(np.float32) * idv[:, :, None]).astype(np.float32).astype(np.float64)
-    r = np.sign(v) * np.floor(np.abs(v) + 0.5)
-    q = r.astype(np.int64).astype(np.uint8)
+        v = ((x - mn[:, :, None]).astype(np.float32) * idv[:, :, None]).astype(np.float32)
+        r = _round_half_away_f32(v)
+        q = r.astype(np.int64).astype(np.uint8)
     packed = (q[:, :, 0::2] | (q[:, :, 1::2] << 4)).astype(np.uint8)
     out = np.empty((rows, nb * 24), dtype=np.uint8)
     out[:, : nb * 4] = mn.view(np.uint8).reshape(rows, nb * 4)
@@ -98,15 +108,16 @@ def dequantize_q4_0(blocks: np.ndarray) -> np.ndarray:
 
 
 def _direct_q4_0(rng: np.random.Generator, rows: int, k: int, std: float) -> np.ndarray:
-    """Synthesize Q4_0 blocks directly (fast path for 7B/13B-sized benchmark files): nibbles from a
-    rounded Gaussian clipped to [-7, 7] (+8), per-block scale log-normal around the value that gives
-    the requested weight std.  Same byte layout as quantize_q4_0."""
+    """Synthesize Q4_0 blocks directly (fast path for 7B/13B-sized benchmark files).  Each nibble is
+    1 + (a & 7) + (b & 7) for two random bytes a, b: a triangular distribution over 1..15 centred on 8, i.e.
+    weights q-8 in -7..7 with std 3.24 like a real quantized tensor (never the unused value 0).  The per-block
+    scale is log-normal around the value that gives the requested weight std.  Same byte layout as quantize_q4_0."""
     nb = k // QK
     out = np.empty((rows, nb, 20), dtype=np.uint8)
-    q = np.clip(np.rint(rng.standard_normal((rows, nb, 32), dtype=np.float32) * 2.6), -7, 7).astype(np.int8)
-    q = (q + 8).astype(np.uint8)
-    out[:, :, 4:] = q[:, :, 0::2] | (q[:, :, 1::2] << 4)
-    d = (std / 2.6 * np.exp(0.1 * rng.standard_normal((rows, nb), dtype=np.float32))).astype(np.float32)
+    a = rng.integers(0, 256, size=(rows, nb, 16), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(rows, nb, 16), dtype=np.uint8)
+    out[:, :, 4:] = (a & 0x77) + (b & 0x77) + 0x11
+    d = (std / 3.24 * np.exp(0.1 * rng.standard_normal((rows, nb), dtype=np.float32))).astype(np.float32)
     out[:, :, :4] = d.view(np.uint8).reshape(rows, nb, 4)
     return out
 
@@ -179,12 +190,14 @@ def write_synthetic_model(path: str, hp: HParams, seed: int = 0, mode: str = "qu
     files = [path if p == 0 else f"{path}.{p}" for p in range(n_parts)]
     outs = [open(fn, "wb") for fn in files]
     total = 0
+    pool = ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
     try:
         for f in outs:
             write_header(f, hp, vocab)
         for name, rows, cols, split in tensor_names(hp):
-            rng = np.random.default_rng([seed] + list(name.encode()))
+            key = [seed] + list(name.encode())
             if cols is None:   # 1-D norm weight, f32, replicated in every part (PO.mm:446-457)
+                rng = np.random.default_rng(key)
                 w = (1.0 + 0.1 * rng.standard_normal(rows)).astype(np.float32)
                 for f in outs:
                     write_tensor_header(f, name, 1, FTYPE_F32, [rows])
@@ -195,29 +208,26 @@ def write_synthetic_model(path: str, hp: HParams, seed: int = 0, mode: str = "qu
                 std *= resid_scale
             if name.startswith("tok_embeddings"):
                 std = 1.0
-            # generate in row chunks to bound memory at 7B/13B sizes
-            chunk = max(1, (64 << 20) // (cols * 4))
             for p, f in enumerate(outs):
-                if split == 0:
-                    pr, pc = rows, cols // n_parts
-                else:
-                    pr, pc = rows // n_parts, cols
+                pr, pc = (rows, cols // n_parts) if split == 0 else (rows // n_parts, cols)
                 write_tensor_header(f, name, 2, hp.ftype, [pc, pr])
-            for r0 in range(0, rows, chunk):
-                r1 = min(rows, r0 + chunk)
+            # row chunks are generated (and quantized) in parallel; each chunk has its own seeded stream, so the
+            # file does not depend on the worker count
+            chunk = max(1, (16 << 20) // (cols * 4))
+            ranges = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
+
+            def make(rr, key=key, std=std, cols=cols):
+                r0, r1 = rr
+                rng = np.random.default_rng(key + [r0])
                 if mode == "direct":
-                    blk = _direct_q4_0(rng, r1 - r0, cols, std)          # [r, nb, 20]
-                    q = blk.reshape(r1 - r0, -1)
-                    per_block = 20
-                else:
-                    w = (rng.standard_normal((r1 - r0, cols), dtype=np.float32) * np.float32(std))
-                    w = w.astype(np.float16).astype(np.float32)
-                    if hp.ftype == FTYPE_Q4_0:
-                        q = quantize_q4_0(w).reshape(r1 - r0, -1)
-                        per_block = 20
-                    else:
-                        q = None
-                        per_block = 24
+                    return None, _direct_q4_0(rng, r1 - r0, cols, std).reshape(r1 - r0, -1)
+                w = (rng.standard_normal((r1 - r0, cols), dtype=np.float32) * np.float32(std))
+                w = w.astype(np.float16).astype(np.float32)
+                if hp.ftype == FTYPE_Q4_0:
+                    return None, quantize_q4_0(w).reshape(r1 - r0, -1)
+                return w, None
+
+            for (r0, r1), (w, q) in zip(ranges, pool.map(make, ranges)):
                 for p, f in enumerate(outs):
                     if split == 1:
                         # rows [p*rows/n_parts, (p+1)*rows/n_parts) live in part p (PO.mm:478-487)
@@ -233,14 +243,14 @@ def write_synthetic_model(path: str, hp: HParams, seed: int = 0, mode: str = "qu
                         # columns [p*cols/n_parts, ...) of every row live in part p (PO.mm:467-477)
                         c0, c1 = p * (cols // n_parts), (p + 1) * (cols // n_parts)
                         if hp.ftype == FTYPE_Q4_0:
-                            b0, b1 = c0 // QK * per_block, c1 // QK * per_block
-                            f.write(np.ascontiguousarray(q[:, b0:b1]).tobytes())
+                            f.write(np.ascontiguousarray(q[:, c0 // QK * 20: c1 // QK * 20]).tobytes())
                         else:
                             # Q4_1 rows are SoA per row, so a column slice is quantized on its own
                             f.write(quantize_q4_1(w[:, c0:c1]).tobytes())
         for f in outs:
             total += f.tell()
     finally:
+        pool.shutdown()
         for f in outs:
             f.close()
     return {"files": files, "bytes": total}
