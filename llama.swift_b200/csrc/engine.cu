@@ -20,6 +20,7 @@
 
 #include "../../include/b200_llama.h"
 #include "kernels.cuh"
+#include "megakernel.cuh"
 
 namespace b200 {
 void host_build_tables(uint16_t *table_silu_f16, uint16_t *table_exp_f16);
@@ -62,6 +63,8 @@ int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 24576) & ~127; }
+
 // Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
 GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   GemvPlan p;
@@ -76,8 +79,8 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   while (p.rmax * (4 / lp) > 512 && lp < 4) lp *= 2;
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
-  const int chunk_target = env_int("B200_CHUNK_BYTES", 16384);
-  p.cb = std::max(1, std::min(p.nb, (chunk_target + p.rmax * 10) / (p.rmax * 20)));
+  // one ring-stage holds one chunk in both the per-matrix kernels and the whole-token kernel
+  p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 20)));
   p.stage_bytes = (p.cb * p.rmax * 20 + 127) & ~127;
   const int nchunks = (p.nb + p.cb - 1) / p.cb;
   const size_t fixed = (size_t) p.nb * 64 + (size_t) ((p.nb + 3) & ~3) * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
@@ -130,6 +133,7 @@ cudaError_t configure_kernels() {
   if ((e = configure_gemv<PRO_NORM, EPI_SILU_MUL>()) != cudaSuccess) return e;
   if ((e = configure_gemv<PRO_NORM, EPI_STORE>()) != cudaSuccess) return e;
   if ((e = configure_gemv<PRO_PLAIN, EPI_STORE>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(decode_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
@@ -191,7 +195,13 @@ struct b200_llama {
   long long weight_bytes = 0;
   long long last_launches = 0;
 
-  int opt_graph = 1, opt_pdl = 0;
+  // whole-token persistent kernel
+  LayerDesc *d_layer_desc = nullptr;
+  unsigned int *d_bar = nullptr;
+  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
+  size_t mega_smem = 0;
+
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
 };
@@ -203,7 +213,44 @@ int attn_smem_bytes(const b200_llama *m, int n_threads) {
 }
 
 // One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
+MatDesc mat_desc(const GemvPlan &p) {
+  MatDesc d = {};
+  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp;
+  return d;
+}
+
+bool mega_usable(const b200_llama *m, int n_threads) {
+  return m->opt_mega && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
+}
+
+// The whole token as ONE cooperative launch of the persistent kernel (megakernel.cuh).
+cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches) {
+  cudaError_t e = cudaMemsetAsync(m->d_bar, 0, sizeof(unsigned int), m->stream);
+  if (e != cudaSuccess) return e;
+  TokenArgs a = {};
+  a.layers = m->d_layer_desc; a.n_layer = m->n_layer; a.out = mat_desc(m->out); a.final_norm = m->d_norm;
+  a.tok_emb = m->d_tok_emb; a.inpL = m->d_inpL; a.inpFF = m->d_inpFF; a.q = m->d_q; a.att = m->d_att; a.h = m->d_h;
+  a.logits = m->d_logits; a.rope = m->d_rope; a.silu_table = m->d_silu; a.exp_table = m->d_exp; a.sp = m->d_sp;
+  a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
+  a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
+  a.xs_floats = m->mega_xs_floats;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(m->n_sm);
+  cfg.blockDim = dim3(MEGA_THREADS);
+  cfg.dynamicSmemBytes = m->mega_smem;
+  cfg.stream = m->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barriers need it
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, decode_token_kernel, a);
+  if (launches) *launches += 1;
+  return e;
+}
+
 cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *launches) {
+  if (mega_usable(m, n_threads)) return enqueue_token_mega(m, n_threads, launches);
   cudaStream_t st = m->stream;
   cudaError_t e;
   const int E = m->n_embd;
@@ -269,7 +316,8 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
 cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
   const bool pdl = m->opt_pdl != 0;
   if (!m->opt_graph) return enqueue_token(m, n_threads, pdl, launches);
-  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != (int) pdl) {
+  const int key_pdl = (int) pdl | (mega_usable(m, n_threads) ? 2 : 0);
+  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != key_pdl) {
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
@@ -283,9 +331,9 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return e;
     m->graph_threads = n_threads;
-    m->graph_pdl = (int) pdl;
+    m->graph_pdl = key_pdl;
   }
-  if (launches) *launches += 2 + 5LL * m->n_layer;
+  if (launches) *launches += mega_usable(m, n_threads) ? 1 : 2 + 5LL * m->n_layer;
   return cudaGraphLaunch(m->graph_exec, m->stream);
 }
 
@@ -321,6 +369,7 @@ void free_model(b200_llama *m) {
   cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h); cudaFree(m->d_logits);
+  cudaFree(m->d_layer_desc); cudaFree(m->d_bar);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -560,6 +609,32 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   CUDA_TRY(cudaMemset(m->d_sp, 0, sizeof(StepParams)));
   CUDA_TRY(cudaMallocHost(&m->h_logits, (size_t) V * 4));
   CUDA_TRY(configure_kernels());
+  {
+    std::vector<LayerDesc> descs(m->n_layer);
+    for (int i = 0; i < m->n_layer; i++) {
+      descs[i].qkv = mat_desc(m->layers[i].qkv); descs[i].wo = mat_desc(m->layers[i].wo);
+      descs[i].w13 = mat_desc(m->layers[i].w13); descs[i].w2 = mat_desc(m->layers[i].w2);
+      descs[i].attn_norm = m->layers[i].attn_norm; descs[i].ffn_norm = m->layers[i].ffn_norm;
+      descs[i].k_layer = m->d_k + (size_t) i * n_ctx * E; descs[i].v_layer = m->d_v + (size_t) i * n_ctx * E;
+    }
+    CUDA_TRY(cudaMalloc(&m->d_layer_desc, descs.size() * sizeof(LayerDesc)));
+    CUDA_TRY(cudaMemcpy(m->d_layer_desc, descs.data(), descs.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&m->d_bar, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(m->d_bar, 0, sizeof(unsigned int)));
+    // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
+    const int nb_max = std::max(E, F) / 32;
+    m->mega_xs_floats = (std::max(E, n_ctx) + 3) & ~3;
+    m->mega_stage_bytes = stage_bytes_cfg();
+    const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
+                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4;
+    const long ring = (long) kSmemBudget - (long) fixed - 256;
+    m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
+    m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
+    int rmax_all = m->out.rmax;
+    for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
+    if (rmax_all > MEGA_MAX_ROWS || rmax_all * 20 > m->mega_stage_bytes) m->mega_S = 0;   // falls back to per-matrix kernels
+  }
+  m->opt_mega = env_int("B200_MEGA", 1);
   m->opt_graph = env_int("B200_GRAPH", 1);
   m->opt_pdl = env_int("B200_PDL", 0);
 
@@ -689,6 +764,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!m || !key) return -1;
   if (!strcmp(key, "graph")) { m->opt_graph = value; return 0; }
   if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
+  if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
   return -1;
 }
 

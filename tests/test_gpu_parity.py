@@ -61,11 +61,14 @@ def _report(tag, got, want):
     return same, r
 
 
+@pytest.mark.parametrize("mega", [1, 0], ids=["whole-token-kernel", "per-matrix-kernels"])
 @pytest.mark.parametrize("n_threads", [1, 8])
-def test_llama_eval_vs_oracle(oracle_lib, small_model, n_threads):
-    """llama_eval through the C ABI: prompt batches of 4 and 9 tokens, then single-token steps (PO.mm:822-889)."""
+def test_llama_eval_vs_oracle(oracle_lib, small_model, n_threads, mega):
+    """llama_eval through the C ABI: prompt batches of 4 and 9 tokens, then single-token steps (PO.mm:822-889).
+    Both schedulers are checked: the persistent whole-token kernel (default) and the per-matrix kernel sequence."""
     ora = CpuModel(oracle_lib, "ora", small_model, 64)
     gpu = lsb.llama_model_load(small_model, n_ctx=64)
+    gpu.set_option("mega", mega)
     try:
         rng = np.random.default_rng(7)
         n_past, n_exact = 0, 0
@@ -110,10 +113,13 @@ def test_decode_device_teacher_forced(oracle_lib, small_model):
             assert int(toks[i]) == int(want.argmax())
         print(f"[parity] teacher-forced {n_steps} steps: worst rel_l2 {worst:.3e}, {ms:.3f} ms total")
         assert worst <= 1e-3
-        # graph replay and plain launches agree bit for bit
+        # graph replay and plain launches agree bit for bit; so do the two schedulers
         gpu.set_option("graph", 0)
         toks2, logits2, _ = gpu.decode_device(0, int(stream[0]), n_steps, n_threads=8, forced_tokens=stream[1:], want_logits=True)
         assert np.array_equal(bits(logits), bits(logits2)) and np.array_equal(toks, toks2)
+        gpu.set_option("mega", 0)
+        toks3, logits3, _ = gpu.decode_device(0, int(stream[0]), n_steps, n_threads=8, forced_tokens=stream[1:], want_logits=True)
+        assert np.array_equal(bits(logits), bits(logits3)) and np.array_equal(toks, toks3)
     finally:
         ora.free()
         gpu.free()

@@ -16,6 +16,7 @@ ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--n-past", type=int, default=8)
 ap.add_argument("--matvec", action="store_true")
 ap.add_argument("--pdl", type=int, default=0)
+ap.add_argument("--mega", type=int, default=1)
 args = ap.parse_args()
 
 if args.matvec:
@@ -40,6 +41,7 @@ t = time.time()
 m = lsb.llama_model_load(path, n_ctx=args.n_past + args.steps + 8)
 print(f"load: {time.time()-t:.1f}s, weights {m.weight_bytes/1e9:.3f} GB", flush=True)
 m.set_option("pdl", args.pdl)
+m.set_option("mega", args.mega)
 lsb.llama_eval(m, 8, 0, np.arange(3, 3 + args.n_past, dtype=np.int32))
 for rep in range(3):
     toks, _, ms = m.decode_device(args.n_past, 5, args.steps, n_threads=8)
