@@ -74,6 +74,10 @@ long long b200_llama_last_launches(const b200_llama *m);
 long long b200_llama_weight_bytes(const b200_llama *m);
 int b200_llama_set_option(b200_llama *m, const char *key, int value);
 
+/* Development profiler of the whole-token kernel: evaluates one token at position pos and returns per-CTA
+ * %globaltimer stamps (ns) at every phase boundary: out[cta * marks + i].  Returns marks (< 0 on error). */
+int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta);
+
 /* Stand-alone kernels behind the same ABI, for kernel-level parity tests (level 1):
  * out[M] = W[M x K] (Q4_0, ggml row layout) * x[K] computed exactly as ggml_compute_forward_mul_mat_q4_0_f32 does. */
 int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out,

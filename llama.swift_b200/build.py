@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libb200llama.so")
-SRCS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "host_math.cpp", "kernels.cuh", "ptx.cuh")]
+SRCS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
 SRCS.append(os.path.join(HERE, "..", "include", "b200_llama.h"))
 
 

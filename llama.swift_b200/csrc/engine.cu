@@ -76,7 +76,7 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   p.rmax = 4 * ((p.g_total + p.n_cta - 1) / p.n_cta);
   int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);
   if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
-  while (p.rmax * (4 / lp) > 512 && lp < 4) lp *= 2;
+  while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
   // one ring-stage holds one chunk in both the per-matrix kernels and the whole-token kernel
@@ -196,12 +196,14 @@ struct b200_llama {
   long long last_launches = 0;
 
   // whole-token persistent kernel
+  long long *d_prof = nullptr;
+  int prof_marks = 0;
   LayerDesc *d_layer_desc = nullptr;
   unsigned int *d_bar = nullptr;
   int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
   size_t mega_smem = 0;
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 16;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
 };
@@ -234,6 +236,8 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
+  a.prof = m->d_prof; a.prof_marks = m->prof_marks;
+  a.l2_ahead = m->opt_l2_ahead;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(m->n_sm);
   cfg.blockDim = dim3(MEGA_THREADS);
@@ -623,18 +627,23 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     CUDA_TRY(cudaMemset(m->d_bar, 0, sizeof(unsigned int)));
     // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
     const int nb_max = std::max(E, F) / 32;
-    m->mega_xs_floats = (std::max(E, n_ctx) + 3) & ~3;
+    m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
     const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
-                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4;
+                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 16;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
-    if (rmax_all > MEGA_MAX_ROWS || rmax_all * 20 > m->mega_stage_bytes) m->mega_S = 0;   // falls back to per-matrix kernels
+    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS;
+    auto rows_fit = [&](const GemvPlan &p) { return p.rmax * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
+    fits = fits && rows_fit(m->out);
+    for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);
+    if (!fits) m->mega_S = 0;   // falls back to the per-matrix kernels
   }
   m->opt_mega = env_int("B200_MEGA", 1);
+  m->opt_l2_ahead = env_int("B200_L2_AHEAD", 16);
   m->opt_graph = env_int("B200_GRAPH", 1);
   m->opt_pdl = env_int("B200_PDL", 0);
 
@@ -760,11 +769,34 @@ int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const 
 long long b200_llama_last_launches(const b200_llama *m) { return m->last_launches; }
 long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes; }
 
+/* Development profiler: run ONE token (current step scalars) through the whole-token kernel with per-CTA globaltimer
+ * stamps at every phase boundary.  out receives n_cta * marks int64 nanosecond stamps; returns marks (or < 0). */
+int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta) {
+  if (!m || !mega_usable(m, n_threads)) return -1;
+  cudaSetDevice(m->device);
+  const int marks = 2 + 15 * m->n_layer + 4;
+  if ((long long) marks * m->n_sm > cap) return -2;
+  if (cudaMalloc(&m->d_prof, (size_t) marks * m->n_sm * 8) != cudaSuccess) return -3;
+  cudaMemset(m->d_prof, 0, (size_t) marks * m->n_sm * 8);
+  m->prof_marks = marks;
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, pos + 1, 0);
+  long long dummy = 0;
+  cudaError_t e = enqueue_token_mega(m, n_threads, &dummy);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out, m->d_prof, (size_t) marks * m->n_sm * 8, cudaMemcpyDeviceToHost);
+  cudaFree(m->d_prof);
+  m->d_prof = nullptr;
+  m->prof_marks = 0;
+  if (n_cta) *n_cta = m->n_sm;
+  return e == cudaSuccess ? marks : -4;
+}
+
 int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!m || !key) return -1;
   if (!strcmp(key, "graph")) { m->opt_graph = value; return 0; }
   if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
   if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
+  if (!strcmp(key, "l2_ahead")) { m->opt_l2_ahead = value; if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; } return 0; }
   return -1;
 }
 

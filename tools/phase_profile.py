@@ -1,0 +1,54 @@
+"""Per-phase timeline of the whole-token kernel from its built-in %globaltimer stamps (development aid).
+Prints, averaged over layers, how long each segment takes for the median CTA and for the slowest CTA."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import llama_swift_b200 as lsb
+from llama_swift_b200 import ggml_format as gf
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--layers", type=int, default=8)
+ap.add_argument("--pos", type=int, default=64)
+ap.add_argument("--out", default="")
+args = ap.parse_args()
+path = f"/tmp/probe-7b-l{args.layers}.bin"
+if not os.path.exists(path):
+    gf.write_synthetic_model(path, gf.HParams(n_layer=args.layers), seed=0, mode="direct")
+m = lsb.llama_model_load(path, n_ctx=max(128, args.pos + 8))
+lsb.llama_eval(m, 8, 0, np.arange(3, 11, dtype=np.int32))
+toks, _, ms = m.decode_device(8, 5, args.pos - 8, n_threads=8)     # fill the cache up to pos
+print(f"decode {args.pos - 8} steps: {ms / (args.pos - 8) * 1e3:.1f} us/token")
+L = lsb.lib()
+L.b200_llama_profile_token.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+cap = 148 * (2 + 15 * args.layers + 4) + 1024
+buf = np.zeros(cap, dtype=np.int64)
+ncta = C.c_int(0)
+for rep in range(3):
+    marks = L.b200_llama_profile_token(m._h, 8, 5, args.pos, buf.ctypes.data, cap, C.byref(ncta))
+assert marks > 0, marks
+t = buf[: ncta.value * marks].reshape(ncta.value, marks).astype(np.float64)
+t = (t - t[:, 0].min()) / 1e3   # us
+names = ["qkv prologue", "qkv rows", "qkv epilogue", "barrier1", "attention", "barrier2", "wo prologue", "wo rows",
+         "wo epi+barrier3", "w13 prologue", "w13 rows", "w13 epi+barrier4", "w2 prologue", "w2 rows", "w2 epi+barrier5"]
+nl = args.layers
+print(f"layers {nl} pos {args.pos}: kernel span {t[:, 15 * nl + 3].max():.1f} us; "
+      f"per layer {(t[:, 15 * nl].max() - t[:, 0].min()) / nl:.2f} us")
+seg = np.zeros((nl, 15, ncta.value))
+for il in range(nl):
+    for k in range(15):
+        seg[il, k] = t[:, 15 * il + k + 1] - t[:, 15 * il + k]
+for k, n in enumerate(names):
+    med = np.median(seg[1:, k, :])
+    mx = np.mean(np.max(seg[1:, k, :], axis=1))
+    mn = np.mean(np.min(seg[1:, k, :], axis=1))
+    print(f"{n:>18}: median CTA {med:6.2f} us   slowest CTA {mx:6.2f} us   fastest {mn:6.2f} us")
+print(f"{'sum of medians':>18}: {sum(np.median(seg[1:, k, :]) for k in range(15)):.2f} us/layer")
+o = 15 * nl
+print(f"output: prologue {np.median(t[:, o + 1] - t[:, o]):.2f}  rows {np.median(t[:, o + 2] - t[:, o + 1]):.2f}  store {np.median(t[:, o + 3] - t[:, o + 2]):.2f} us (median CTA)")
+if args.out:
+    np.save(args.out, t)
