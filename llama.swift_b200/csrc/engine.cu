@@ -74,7 +74,8 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   p.g_total = Mpad / 4;
   p.n_cta = std::min(n_sm, p.g_total);
   p.rmax = 4 * ((p.g_total + p.n_cta - 1) / p.n_cta);
-  int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);
+  // as many threads per row as fit the 512 compute threads: the row loops are latency-bound, more warps hide more
+  int lp = p.rmax * 4 <= MEGA_COMPUTE_THREADS ? 1 : (p.rmax * 2 <= MEGA_COMPUTE_THREADS ? 2 : 4);
   if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
   while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;
   p.lp = lp;
@@ -198,12 +199,12 @@ struct b200_llama {
   // whole-token persistent kernel
   long long *d_prof = nullptr;
   int prof_marks = 0;
-  LayerDesc *d_layer_desc = nullptr;
+  TokenArgs *h_token_args = nullptr;   // host copy of the kernel parameter block (layer descriptors prefilled)
   unsigned int *d_bar = nullptr;
   int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
   size_t mega_smem = 0;
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 16;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
 };
@@ -229,8 +230,8 @@ bool mega_usable(const b200_llama *m, int n_threads) {
 cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches) {
   cudaError_t e = cudaMemsetAsync(m->d_bar, 0, sizeof(unsigned int), m->stream);
   if (e != cudaSuccess) return e;
-  TokenArgs a = {};
-  a.layers = m->d_layer_desc; a.n_layer = m->n_layer; a.out = mat_desc(m->out); a.final_norm = m->d_norm;
+  TokenArgs &a = *m->h_token_args;     // descriptors were filled in at load time
+  a.n_layer = m->n_layer; a.out = mat_desc(m->out); a.final_norm = m->d_norm;
   a.tok_emb = m->d_tok_emb; a.inpL = m->d_inpL; a.inpFF = m->d_inpFF; a.q = m->d_q; a.att = m->d_att; a.h = m->d_h;
   a.logits = m->d_logits; a.rope = m->d_rope; a.silu_table = m->d_silu; a.exp_table = m->d_exp; a.sp = m->d_sp;
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
@@ -373,7 +374,7 @@ void free_model(b200_llama *m) {
   cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h); cudaFree(m->d_logits);
-  cudaFree(m->d_layer_desc); cudaFree(m->d_bar);
+  delete m->h_token_args; cudaFree(m->d_bar);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -621,8 +622,9 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
       descs[i].attn_norm = m->layers[i].attn_norm; descs[i].ffn_norm = m->layers[i].ffn_norm;
       descs[i].k_layer = m->d_k + (size_t) i * n_ctx * E; descs[i].v_layer = m->d_v + (size_t) i * n_ctx * E;
     }
-    CUDA_TRY(cudaMalloc(&m->d_layer_desc, descs.size() * sizeof(LayerDesc)));
-    CUDA_TRY(cudaMemcpy(m->d_layer_desc, descs.data(), descs.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice));
+    m->h_token_args = new TokenArgs();
+    memset(m->h_token_args, 0, sizeof(TokenArgs));
+    if (m->n_layer <= MEGA_MAX_LAYERS) memcpy(m->h_token_args->layers, descs.data(), descs.size() * sizeof(LayerDesc));
     CUDA_TRY(cudaMalloc(&m->d_bar, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(m->d_bar, 0, sizeof(unsigned int)));
     // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
@@ -636,14 +638,14 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
-    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS;
+    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS;
     auto rows_fit = [&](const GemvPlan &p) { return p.rmax * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
     fits = fits && rows_fit(m->out);
     for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);
     if (!fits) m->mega_S = 0;   // falls back to the per-matrix kernels
   }
   m->opt_mega = env_int("B200_MEGA", 1);
-  m->opt_l2_ahead = env_int("B200_L2_AHEAD", 16);
+  m->opt_l2_ahead = env_int("B200_L2_AHEAD", 0);
   m->opt_graph = env_int("B200_GRAPH", 1);
   m->opt_pdl = env_int("B200_PDL", 0);
 

@@ -35,8 +35,10 @@ struct LayerDesc {
   float *k_layer, *v_layer;
 };
 
+constexpr int MEGA_MAX_LAYERS = 80;   // LLaMA-65B; the descriptors ride in the (large, CUDA >= 12.1) kernel parameter block
+
 struct TokenArgs {
-  const LayerDesc *layers;
+  LayerDesc layers[MEGA_MAX_LAYERS];   // in the constant bank: descriptor fields cost no registers and no loads
   int n_layer;
   MatDesc out;
   const float *final_norm;
@@ -55,12 +57,12 @@ struct TokenArgs {
   int prof_marks;
 };
 
-constexpr int MEGA_COMPUTE_WARPS = 14;
-constexpr int MEGA_COMPUTE_THREADS = MEGA_COMPUTE_WARPS * 32;   // 448
-constexpr int MEGA_THREADS = MEGA_COMPUTE_THREADS + 64;          // + loader warp + L2-prefetch warp = 512 -> 128 regs/thread
-constexpr int MEGA_MAX_ROWS = 448;     // rows per CTA upper bound (rowres[])
+constexpr int MEGA_COMPUTE_WARPS = 16;
+constexpr int MEGA_COMPUTE_THREADS = MEGA_COMPUTE_WARPS * 32;   // 512: one 8-float item per thread at n_embd 4096
+constexpr int MEGA_THREADS = MEGA_COMPUTE_THREADS + 32;          // + the TMA loader warp (96 regs/thread)
+constexpr int MEGA_MAX_ROWS = 512;     // rows per CTA upper bound (rowres[])
 constexpr int MEGA_MAX_NTH = 16;       // reference thread counts supported by the V*P partition
-constexpr int MEGA_NORM_ROUNDS = 3;    // 8-element items per thread held in registers by the LayerNorm prologue (K <= 10752)
+constexpr int MEGA_NORM_ROUNDS = 2;    // 8-element items per thread held in registers by the LayerNorm prologue (K <= 7168)
 
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
@@ -264,7 +266,7 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 // warps per scheduler (small-M matrices) nothing else hides the LDS latency.
 template <int LP>
 struct GemvGroup {
-  static constexpr int G = LP == 1 ? 4 : (LP == 2 ? 2 : 1);
+  static constexpr int G = 4;   // blocks per software-pipeline group (used by the LP = 1 row loop)
   uint32_t w[G * LP];     // [g][j] -> w[g * LP + j]
   uint4 x[G * LP];
   float sc[G], dx[G];
@@ -310,33 +312,11 @@ __device__ __forceinline__ void group_compute(const GemvGroup<LP> &gr, u64 (&acc
   }
 }
 
-// Out-of-line on purpose: each LP variant gets its own register allocation (inlined 15x into the token kernel the
-// pipelined loop spilled).  Shared-memory areas travel as 32-bit shared-window offsets and are turned back into
-// pointers here, which keeps the address space visible to the compiler (LDS, not generic LD).
-struct GemvCall {
-  uint32_t stages, xq, dxs, rowres, full, empty;   // shared-window addresses
-  int nb, cb, R, S, stage_bytes;
-};
-
-struct GemvSm {
-  const uint8_t *stages;
-  const uint4 *xq;
-  const float *dxs;
-  float *rowres;
-  uint64_t *full, *empty;
-};
-
 template <int LP>
-__device__ __noinline__ uint32_t gemv_rows(const GemvCall c, uint32_t gchunk, const int tid) {
-  constexpr int UPR = 4 / LP, G = GemvGroup<LP>::G;
-  GemvSm sm;
-  sm.stages = reinterpret_cast<const uint8_t *>(__cvta_shared_to_generic(c.stages));
-  sm.xq = reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(c.xq));
-  sm.dxs = reinterpret_cast<const float *>(__cvta_shared_to_generic(c.dxs));
-  sm.rowres = reinterpret_cast<float *>(__cvta_shared_to_generic(c.rowres));
-  sm.full = reinterpret_cast<uint64_t *>(__cvta_shared_to_generic(c.full));
-  sm.empty = reinterpret_cast<uint64_t *>(__cvta_shared_to_generic(c.empty));
-  const int R = c.R, nb = c.nb, cb = c.cb, S = c.S, stage_bytes = c.stage_bytes;
+__device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, uint32_t &gchunk,
+                                          int S, int stage_bytes, int tid) {
+  constexpr int UPR = 4 / LP;
+  const int R = rp.R, nb = md.nb, cb = md.cb;
   const int nchunks = (nb + cb - 1) / cb;
   const bool active = tid < R * UPR;
   const int r = active ? tid / UPR : R - 1;
@@ -359,30 +339,55 @@ __device__ __noinline__ uint32_t gemv_rows(const GemvCall c, uint32_t gchunk, co
       const float *sc = reinterpret_cast<const float *>(st + cbk * R * 16) + r;
       const uint4 *xqk = sm.xq + k * cb * 4 + pg * LP;
       const float *dxk = sm.dxs + k * cb;
-      const int ngroups = cbk / G;
-      GemvGroup<LP> ga, gb;
-      if (ngroups > 0) group_load<LP>(ga, nib, sc, xqk, dxk, wstride, R);
-      int g = 0;
-      for (; g + 2 <= ngroups; g += 2) {
-        group_load<LP>(gb, nib + (g + 1) * G * wstride, sc + (g + 1) * G * R, xqk + (g + 1) * G * 4, dxk + (g + 1) * G, wstride, R);
-        group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
-        if (g + 2 < ngroups)
-          group_load<LP>(ga, nib + (g + 2) * G * wstride, sc + (g + 2) * G * R, xqk + (g + 2) * G * 4, dxk + (g + 2) * G, wstride, R);
-        group_compute<LP>(gb, acc, cvt_mul, cvt_sub);
-      }
-      if (g < ngroups) group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
-      for (int bl = ngroups * G; bl < cbk; bl++) {   // leftover blocks (cbk not a multiple of G)
-        const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);
-#pragma unroll
-        for (int j = 0; j < LP; j++) {
-          const uint32_t wv = nib[bl * wstride + j];
-          const uint4 xv = xqk[bl * 4 + j];
+      if constexpr (LP == 1) {
+        // 3-4 resident warps per SM on the small-M matrices: nothing but ILP hides the LDS latency, so the operands of
+        // the next group of 4 blocks are fetched into a second register set while the current group is computed
+        constexpr int G = GemvGroup<LP>::G;
+        const int ngroups = cbk / G;
+        GemvGroup<LP> ga, gb;
+        if (ngroups > 0) group_load<LP>(ga, nib, sc, xqk, dxk, wstride, R);
+        int g = 0;
+        for (; g + 2 <= ngroups; g += 2) {
+          group_load<LP>(gb, nib + (g + 1) * G * wstride, sc + (g + 1) * G * R, xqk + (g + 1) * G * 4, dxk + (g + 1) * G, wstride, R);
+          group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
+          if (g + 2 < ngroups)
+            group_load<LP>(ga, nib + (g + 2) * G * wstride, sc + (g + 2) * G * R, xqk + (g + 2) * G * 4, dxk + (g + 2) * G, wstride, R);
+          group_compute<LP>(gb, acc, cvt_mul, cvt_sub);
+        }
+        if (g < ngroups) group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
+        for (int bl = ngroups * G; bl < cbk; bl++) {   // leftover blocks
+          const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);
+          const uint32_t wv = nib[bl * wstride];
+          const uint4 xv = xqk[bl * 4];
           const int ia = dp4a_us(wv & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
           const int ib = dp4a_us(wv & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
           const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
-          acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);
+          acc[0] = ffma2(pack_f2(sdx, sdx), f, acc[0]);
+        }
+      } else {
+#pragma unroll 4
+      for (int bl = 0; bl < cbk; bl++) {
+        uint32_t wv[LP];
+        if constexpr (LP == 4) {
+          const uint4 t = *reinterpret_cast<const uint4 *>(nib + bl * wstride);
+          wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+        } else if constexpr (LP == 2) {
+          const uint2 t = *reinterpret_cast<const uint2 *>(nib + bl * wstride);
+          wv[0] = t.x; wv[1] = t.y;
+        } else {
+          wv[0] = nib[bl * wstride];
+        }
+        const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);                        // _mm256_mul_ps(d0, d1), ggml.c:1431
+#pragma unroll
+        for (int j = 0; j < LP; j++) {
+          const uint4 xv = xqk[bl * 4 + j];
+          const int ia = dp4a_us(wv[j] & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);   // float bits of 12582912 + isum(lane 2p)
+          const int ib = dp4a_us(wv[j] & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);   // float bits of 12582912 + 16*isum(lane 2p+1)
+          const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                 // exact (float)isum for both lanes
+          acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                           // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
         }
       }
+          }
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
@@ -411,20 +416,15 @@ __device__ __noinline__ uint32_t gemv_rows(const GemvCall c, uint32_t gchunk, co
   }
   if (active && pg == 0) sm.rowres[r] = res;
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
-  return gchunk;
 }
 
 __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, uint32_t &gchunk,
                                               int S, int stage_bytes, int tid) {
   if (rp.R == 0) { named_bar_sync(1, MEGA_COMPUTE_THREADS); return; }
-  GemvCall c;
-  c.stages = smem_u32(sm.stages); c.xq = smem_u32(sm.xq); c.dxs = smem_u32(sm.dxs); c.rowres = smem_u32(sm.rowres);
-  c.full = smem_u32(sm.full); c.empty = smem_u32(sm.empty);
-  c.nb = md.nb; c.cb = md.cb; c.R = rp.R; c.S = S; c.stage_bytes = stage_bytes;
   switch (md.lp) {
-    case 1: gchunk = gemv_rows<1>(c, gchunk, tid); break;
-    case 2: gchunk = gemv_rows<2>(c, gchunk, tid); break;
-    default: gchunk = gemv_rows<4>(c, gchunk, tid); break;
+    case 1: gemv_rows<1>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
+    case 2: gemv_rows<2>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
+    default: gemv_rows<4>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
   }
 }
 
@@ -441,7 +441,6 @@ __device__ __forceinline__ void stream_matrix(const MatDesc &md, const MegaSmem 
     const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
     mbar_arrive_expect_tx(&sm.full[s], bytes);
     tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
-    *sm.loader_g = gchunk + 1;
   }
 }
 
@@ -544,15 +543,14 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   }
 }
 
-__global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const TokenArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_mega[];
-  const int tid = threadIdx.x;
-  const int S = a.S, stage_bytes = a.stage_bytes;
-  const int nb_max = max(a.n_embd, a.n_ff) / 32;
+extern __shared__ __align__(128) uint8_t smem_mega[];
 
+__device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
+  const int S = a.S;
+  const int nb_max = max(a.n_embd, a.n_ff) / 32;
   MegaSmem sm;
   sm.stages = smem_mega;
-  sm.xq = reinterpret_cast<uint4 *>(smem_mega + (size_t) S * stage_bytes);
+  sm.xq = reinterpret_cast<uint4 *>(smem_mega + (size_t) S * a.stage_bytes);
   sm.dxs = reinterpret_cast<float *>(sm.xq + (size_t) nb_max * 4);
   sm.xs = sm.dxs + ((nb_max + 3) & ~3);
   sm.rowres = sm.xs + a.xs_floats;
@@ -562,6 +560,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const Tok
   sm.full = reinterpret_cast<uint64_t *>(sm.part + MEGA_MAX_NTH * 32);
   sm.empty = sm.full + S;
   sm.loader_g = reinterpret_cast<volatile uint32_t *>(sm.empty + S);
+  return sm;
+}
+
+#undef PROF_MARK
+#define PROF_MARK() do { if (a.prof && tid == 0 && pm < a.prof_marks) a.prof[(size_t) blockIdx.x * a.prof_marks + pm] = globaltimer_ns(); pm++; } while (0)
+
+enum PhaseKind { PH_QKV = 0, PH_ATTN = 1, PH_WO = 2, PH_W13 = 3, PH_W2 = 4, PH_OUT = 5 };
+
+__global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __grid_constant__ TokenArgs a) {
+  const int tid = threadIdx.x;
+  const int S = a.S, stage_bytes = a.stage_bytes;
+  const MegaSmem sm = carve_smem(a);
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], MEGA_COMPUTE_WARPS); }
@@ -575,78 +585,94 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const Tok
       // ===== TMA loader: the whole token's weight stream for this SM, in schedule order =====
       uint32_t g = 0;
       for (int il = 0; il < a.n_layer; il++) {
-        const LayerDesc &L = a.layers[il];
-        stream_matrix(L.qkv, sm, g, S, stage_bytes);
-        stream_matrix(L.wo, sm, g, S, stage_bytes);
-        stream_matrix(L.w13, sm, g, S, stage_bytes);
-        stream_matrix(L.w2, sm, g, S, stage_bytes);
+        stream_matrix(a.layers[il].qkv, sm, g, S, stage_bytes);
+        stream_matrix(a.layers[il].wo, sm, g, S, stage_bytes);
+        stream_matrix(a.layers[il].w13, sm, g, S, stage_bytes);
+        stream_matrix(a.layers[il].w2, sm, g, S, stage_bytes);
       }
       stream_matrix(a.out, sm, g, S, stage_bytes);
-    } else if (tid == MEGA_COMPUTE_THREADS + 32 && a.l2_ahead > 0) {
-      // ===== L2 prefetcher: same schedule, a bounded distance ahead of the loader =====
-      uint32_t g = 0;
-      for (int il = 0; il < a.n_layer; il++) {
-        const LayerDesc &L = a.layers[il];
-        prefetch_matrix(L.qkv, sm, g, S, a.l2_ahead);
-        prefetch_matrix(L.wo, sm, g, S, a.l2_ahead);
-        prefetch_matrix(L.w13, sm, g, S, a.l2_ahead);
-        prefetch_matrix(L.w2, sm, g, S, a.l2_ahead);
-      }
-      prefetch_matrix(a.out, sm, g, S, a.l2_ahead);
     }
     return;
   }
 
   // ===== compute warps =====
+  // ONE loop over the token's phases with a single instance of the row loops: the kind of phase only selects the
+  // prologue (how the activation vector is produced and quantized) and the epilogue (the graph nodes that consume the
+  // mat-vec).  Descriptors come from the kernel parameter block (constant bank).
   const int E = a.n_embd, HD = E / a.n_head;
-  const int pos = a.sp->pos, p_part = a.sp->p_part, token = a.sp->token;
+  const int pos = a.sp->pos;
   uint32_t gchunk = 0;
   unsigned int phase = 0;
   int pm = 0;
   PROF_MARK();   // 0: kernel start
-  double xd[MEGA_NORM_ROUNDS][8];
+  const int n_steps = 5 * a.n_layer + 1;
+  for (int step = 0; step < n_steps; step++) {
+    const int il = step / 5;
+    const int kind = il < a.n_layer ? step - 5 * il : PH_OUT;
+    const LayerDesc &L = a.layers[il < a.n_layer ? il : 0];
 
-  // get_rows: dequantize_row_q4_0 of the token's embedding row (ggml.c:6760-6785, 651-684) straight into registers
-  {
-    const uint8_t *row = a.tok_emb + (size_t) token * (E / 32) * 20;
-    const int items = E / 8;
+    if (kind == PH_ATTN) {
+      // ---- attention (PO.mm:614-646) on the first 4*n_head CTAs ----
+      if ((int) blockIdx.x < 4 * a.n_head) attention_phase(a, L, sm, blockIdx.x >> 2, blockIdx.x & 3, pos, a.sp->p_part, tid);
+      PROF_MARK();
+      grid_barrier(a.bar, phase, tid);
+      PROF_MARK();
+      continue;
+    }
+
+    // ---- prologue ----
+    const MatDesc &md = kind == PH_QKV ? L.qkv : kind == PH_WO ? L.wo : kind == PH_W13 ? L.w13 : kind == PH_W2 ? L.w2 : a.out;
+    if (kind == PH_WO) {
+      prologue_plain(a.att, E / 32, sm, tid);                                   // PO.mm:649-651
+    } else if (kind == PH_W2) {
+      prologue_plain(a.h, a.n_ff / 32, sm, tid);                                // PO.mm:682-684
+    } else {
+      double xd[MEGA_NORM_ROUNDS][8];
+      if (step == 0) {
+        // get_rows: dequantize_row_q4_0 of the token's embedding row (ggml.c:6760-6785, 651-684) straight into registers
+        const uint8_t *row = a.tok_emb + (size_t) a.sp->token * (E / 32) * 20;
+        const int items = E / 8;
 #pragma unroll
-    for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
-      const int it = tid + rd * MEGA_COMPUTE_THREADS;
-      if (it < items) {
-        const uint8_t *blk = row + (it >> 2) * 20;
-        const float d = __ldg(reinterpret_cast<const float *>(blk));
-        const uint32_t by = __ldg(reinterpret_cast<const uint32_t *>(blk + 4) + (it & 3));   // 4 bytes = 8 nibbles
+        for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
+          const int it = tid + rd * MEGA_COMPUTE_THREADS;
+          if (it < items) {
+            const uint8_t *blk = row + (it >> 2) * 20;
+            const float d = __ldg(reinterpret_cast<const float *>(blk));
+            const uint32_t by = __ldg(reinterpret_cast<const uint32_t *>(blk + 4) + (it & 3));   // 4 bytes = 8 nibbles
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int qn = (by >> (4 * i)) & 0xf;                 // element 2j = low nibble of byte j, 2j+1 = high nibble
-          const float v = __fmul_rn((float) (qn - 8), d);
-          xd[rd][i] = v;
-          if (blockIdx.x == 0) a.inpL[it * 8 + i] = v;          // residual source for layer 0 (read after two grid barriers)
+            for (int i = 0; i < 8; i++) {
+              const int qn = (by >> (4 * i)) & 0xf;             // element 2j = low nibble of byte j, 2j+1 = high nibble
+              const float v = __fmul_rn((float) (qn - 8), d);
+              xd[rd][i] = v;
+              if (blockIdx.x == 0) a.inpL[it * 8 + i] = v;      // residual source for layer 0 (read after two grid barriers)
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) xd[rd][i] = 0.0;
+          }
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) xd[rd][i] = 0.0;
+        load_items(xd, kind == PH_W13 ? a.inpFF : a.inpL, E / 32, tid);
       }
+      const float *nw = kind == PH_QKV ? L.attn_norm : kind == PH_W13 ? L.ffn_norm : a.final_norm;
+      prologue_norm_regs(xd, nw, E / 32, sm, tid);                              // PO.mm:570-575, 660-665, 694-701
     }
-  }
+    PROF_MARK();
 
-  for (int il = 0; il < a.n_layer; il++) {
-    const LayerDesc &L = a.layers[il];
-    // ---- phase 1: norm -> wq|wk|wv -> rope -> q buffer + KV cache row (PO.mm:570-611) ----
-    {
-      if (il > 0) load_items(xd, a.inpL, E / 32, tid);
-      prologue_norm_regs(xd, L.attn_norm, E / 32, sm, tid);
-      PROF_MARK();   // +1: qkv prologue done
-      const RowPart rp = row_part(L.qkv.g_total, gridDim.x, blockIdx.x);
-      gemv_dispatch(L.qkv, rp, sm, gchunk, S, stage_bytes, tid);
-      PROF_MARK();   // +2: qkv rows done
+    // ---- the mat-vec ----
+    const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
+    gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, tid);
+    PROF_MARK();
+
+    // ---- epilogue ----
+    if (kind == PH_QKV) {
+      // rope (ggml.c:7110-7127, double math, host-built angles) + KV store (PO.mm:585-611)
       for (int i = tid; i < rp.R / 2; i += MEGA_COMPUTE_THREADS) {
         const int g = rp.row0 + 2 * i;
-        if (g >= L.qkv.M) continue;
+        if (g >= md.M) continue;
         const int which = g / E, col = g - which * E;
         float y0 = sm.rowres[2 * i], y1 = sm.rowres[2 * i + 1];
-        if (which < 2) {   // ggml_rope, ggml.c:7110-7127 (double math, host-built angles)
+        if (which < 2) {
           const double2 cs = a.rope[(size_t) pos * (HD / 2) + (col % HD) / 2];
           const double x0 = y0, x1 = y1;
           y0 = (float) __dsub_rn(__dmul_rn(x0, cs.x), __dmul_rn(x1, cs.y));
@@ -656,78 +682,28 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const Tok
         dst[0] = y0;
         dst[1] = y1;
       }
-      PROF_MARK();   // +3: qkv epilogue done
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();   // +4: barrier 1 passed
-    }
-    // ---- phase 2: attention (PO.mm:614-646) on the first 4*n_head CTAs ----
-    {
-      if ((int) blockIdx.x < 4 * a.n_head) attention_phase(a, L, sm, blockIdx.x >> 2, blockIdx.x & 3, pos, p_part, tid);
-      PROF_MARK();   // +5: attention done
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();   // +6: barrier 2 passed
-    }
-    // ---- phase 3: wo, + inpSA (PO.mm:649-654) ----
-    {
-      prologue_plain(a.att, E / 32, sm, tid);
-      PROF_MARK();   // +7: wo prologue done
-      const RowPart rp = row_part(L.wo.g_total, gridDim.x, blockIdx.x);
-      gemv_dispatch(L.wo, rp, sm, gchunk, S, stage_bytes, tid);
-      PROF_MARK();   // +8: wo rows done
-      for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
-        const int g = rp.row0 + i;
-        if (g < L.wo.M) a.inpFF[g] = __fadd_rn(sm.rowres[i], __ldcg(a.inpL + g));   // ggml_add, PO.mm:654
-      }
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();   // +9: barrier 3 passed
-    }
-    // ---- phase 4: norm -> w1|w3 -> silu(w1 x) * (w3 x) (PO.mm:660-680) ----
-    {
-      load_items(xd, a.inpFF, E / 32, tid);
-      prologue_norm_regs(xd, L.ffn_norm, E / 32, sm, tid);
-      PROF_MARK();   // +10: w13 prologue done
-      const RowPart rp = row_part(L.w13.g_total, gridDim.x, blockIdx.x);
-      gemv_dispatch(L.w13, rp, sm, gchunk, S, stage_bytes, tid);
-      PROF_MARK();   // +11: w13 rows done
+      PROF_MARK();
+    } else if (kind == PH_W13) {
+      // fused rows 2i = w1 row i, 2i+1 = w3 row i: silu(w1 x) * (w3 x), PO.mm:678-680; silu via the fp16 table (ggml.c:1955-1963)
       for (int i = tid; i < rp.R / 2; i += MEGA_COMPUTE_THREADS) {
         const int g = rp.row0 / 2 + i;
-        if (2 * g < L.w13.M) {   // fused rows 2i = w1 row i, 2i+1 = w3 row i; silu via the fp16 table (ggml.c:1955-1963)
+        if (2 * g < md.M) {
           const uint16_t hx = __half_as_ushort(__float2half_rn(sm.rowres[2 * i]));
           const float sv = __half2float(__ushort_as_half(__ldg(a.silu_table + hx)));
           a.h[g] = __fmul_rn(sv, sm.rowres[2 * i + 1]);
         }
       }
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();   // +12: barrier 4 passed
-    }
-    // ---- phase 5: w2, + inpFF (PO.mm:682-687) ----
-    {
-      prologue_plain(a.h, a.n_ff / 32, sm, tid);
-      PROF_MARK();   // +13: w2 prologue done
-      const RowPart rp = row_part(L.w2.g_total, gridDim.x, blockIdx.x);
-      gemv_dispatch(L.w2, rp, sm, gchunk, S, stage_bytes, tid);
-      PROF_MARK();   // +14: w2 rows done
+    } else {
+      // ggml_add with the residual stream (PO.mm:654, 687), or the plain logits store (PO.mm:705)
+      const float *resid = kind == PH_WO ? a.inpL : a.inpFF;
+      float *dst = kind == PH_WO ? a.inpFF : kind == PH_W2 ? a.inpL : a.logits;
       for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
         const int g = rp.row0 + i;
-        if (g < L.w2.M) a.inpL[g] = __fadd_rn(sm.rowres[i], __ldcg(a.inpFF + g));   // ggml_add, PO.mm:687
+        if (g < md.M) dst[g] = kind == PH_OUT ? sm.rowres[i] : __fadd_rn(sm.rowres[i], __ldcg(resid + g));
       }
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();   // +15: barrier 5 passed
     }
-  }
-  // ---- final norm -> output (PO.mm:694-706) ----
-  {
-    load_items(xd, a.inpL, E / 32, tid);
-    prologue_norm_regs(xd, a.final_norm, E / 32, sm, tid);
-    PROF_MARK();   // output prologue done
-    const RowPart rp = row_part(a.out.g_total, gridDim.x, blockIdx.x);
-    gemv_dispatch(a.out, rp, sm, gchunk, S, stage_bytes, tid);
-    PROF_MARK();   // output rows done
-    for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
-      const int g = rp.row0 + i;
-      if (g < a.out.M) a.logits[g] = sm.rowres[i];
-    }
-    PROF_MARK();   // last: logits stored
+    if (kind != PH_OUT) grid_barrier(a.bar, phase, tid);
+    PROF_MARK();
   }
 }
 
