@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric: decode tokens/sec, LLaMA-7B Q4_0, bs = 1, and % of the HBM roofline.
+
+One "step" = one pass of the hot path = llama_eval of ONE token (PO.mm:510-735) at the next position of a
+512-token generation that follows an 8-token prompt (BASELINE.json configs[1]).  Synthetic model: a 7B-shaped file in
+the reference's own "ggml" format (seeded Q4_0 blocks, llama.swift_b200/ggml_format.py) -- no real weights exist here.
+
+  value ............ tokens/s of the device-resident loop (weights, KV cache, token id all in HBM when the clock
+                     starts; greedy arg-max on the GPU feeds the next step), CUDA-event timed on the launching stream
+  e2e .............. the same generation driven through the reference-facing C ABI (b200_llama_eval, the llama_eval
+                     drop-in): per step the token id goes host->device and the 32000 logits come back device->host
+                     (pinned staging inside the library) and the host picks the arg-max
+  roofline ......... dominant kernel = decode_token_kernel (the whole token in one persistent launch): algorithmic
+                     bytes per launch (weights once + norm weights + embedding row + f32 KV
+                     read/write) / its average launch duration from CUDA events around each launch
+  cpu_baseline ..... the reference's own CPU path (oracle/_ref = unmodified ggml.c + llama_eval) on this host's cores
+
+--impl reference times ONLY that CPU path (rank 0; other ranks exit) and prints the same JSON shape.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPT = [1, 15043, 3186, 29892, 590, 1024, 338, 29871]      # 8 fixed ids, BOS first (utils.cpp:284-286)
+N_PROMPT = len(PROMPT)
+
+# algorithmic bytes (BASELINE.md section 2 / SURVEY.md section 8d), LLaMA-7B Q4_0
+W_BYTES = 4_129_423_360
+S_BYTES = 1_064_960 + 2_560
+KV_ROW = 1_048_576            # 2 (K,V) * n_layer * n_embd * 4 B per cached position
+
+
+def algorithmic_bytes(pos: int) -> int:
+    return W_BYTES + S_BYTES + KV_ROW * (pos + 1) + KV_ROW
+
+
+def model_path(layers: int) -> str:
+    d = os.environ.get("B200_BENCH_DIR", "/tmp/b200_bench")
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, "ggml-model-q4_0.bin" if layers == 32 else f"ggml-model-q4_0-l{layers}.bin")
+
+
+def ensure_model(layers: int) -> str:
+    from llama_swift_b200 import ggml_format as gf
+    path = model_path(layers)
+    if not os.path.exists(path):
+        tmp = path + f".tmp{os.getpid()}"
+        gf.write_synthetic_model(tmp, gf.HParams(n_layer=layers), seed=0, mode="direct")
+        os.replace(tmp, path)
+    return path
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+
+
+def ref_lib():
+    so = os.path.join(ROOT, "oracle", "_ref", "libllama_ref.so")
+    if not os.path.exists(so):
+        if os.path.isdir("/root/reference/Sources/cpp"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+        else:
+            return None
+    L = C.CDLL(so)
+    L.ref_llama_load.restype = C.c_void_p
+    L.ref_llama_load.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.ref_llama_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.ref_llama_free.argtypes = [C.c_void_p]
+    return L
+
+
+def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: int):
+    """The reference's own llama_eval on the host: 8-token prompt, then greedy single-token steps.  Returns
+    (tokens/s over the timed decode steps, steps timed, description)."""
+    L = ref_lib()
+    if L is None:
+        return None, 0, "oracle/_ref/libllama_ref.so not available"
+    err = C.create_string_buffer(512)
+    h = L.ref_llama_load(path.encode(), 64, err, 512)
+    if not h:
+        return None, 0, "reference load failed: " + err.value.decode()
+    h = C.c_void_p(h)
+    n_vocab = 32000
+    logits = np.empty(n_vocab, np.float32)
+    toks = np.array(PROMPT, np.int32)
+    L.ref_llama_eval(h, n_threads, 0, toks.ctypes.data, len(toks), logits.ctypes.data, err, 512)   # prompt, untimed
+    n_past, cur = len(toks), int(logits.argmax())
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < max_steps and n_past < 62:
+        t = np.array([cur], np.int32)
+        t0 = time.perf_counter()
+        L.ref_llama_eval(h, n_threads, n_past, t.ctypes.data, 1, logits.ctypes.data, err, 512)
+        times.append(time.perf_counter() - t0)          # the reference's own t_predict_us window (PO.mm:837-845)
+        n_past += 1
+        cur = int(logits.argmax())
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+            break
+    L.ref_llama_free(h)
+    total = sum(times)
+    med = sorted(times)[len(times) // 2]
+    return len(times) / total, len(times), (f"reference ggml CPU path (oracle/_ref, AVX2 build), {n_threads} threads, 8-token prompt then "
+                                             f"{len(times)} greedy decode steps at n_past 8..{n_past - 1}; median {med * 1e3:.1f} ms/token")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="debug: fewer layers (the result is then NOT the benchmark)")
+    ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = args.gpus
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    config = {"workload": "LLaMA-7B Q4_0 bs=1 decode, 512-token gen after an 8-token prompt (BASELINE.json configs[1])",
+              "model_file": "synthetic ggml-format 7B (n_embd 4096, n_layer %d, n_vocab 32000), seed 0" % args.layers,
+              "n_past_start": N_PROMPT, "ref_threads_mirrored": args.threads,
+              "l2_policy": "per-step working set (4.13 GB weights) >> 126 MB L2, no flush needed"}
+    if args.layers != 32:
+        config["workload"] += f" [DEBUG: {args.layers} layers -- not the benchmark]"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        path = ensure_model(args.layers)
+        cores = os.cpu_count() or 1
+        nth = min(cores, 32)
+        tps, n, desc = time_reference_cpu(path, nth, budget_s=150.0, max_steps=max(3, min(steps, 54)))
+        if tps is None:
+            print(json.dumps({"impl": "reference", "unavailable": desc}))
+            return 0
+        line = {"impl": "reference", "metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s",
+                "n_gpus": n_gpus, "steps": n, "warmup": 1, "ms_per_step": 1e3 / tps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int4 x int4 -> int32 block dots, fp32 accumulate (AVX2 CPU)",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": nth, "kind": "reference", "sample": desc},
+                "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import llama_swift_b200 as lsb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        ensure_model(args.layers)
+    if dist is not None:
+        dist.barrier()
+    path = model_path(args.layers)
+
+    n_ctx = N_PROMPT + steps + 8
+    model = lsb.llama_model_load(path, n_ctx=n_ctx, device=local_rank)
+    n_vocab = model.n_vocab
+
+    def prompt():
+        return lsb.llama_eval(model, args.threads, 0, np.array(PROMPT, np.int32))
+
+    # ---- warm-up (untimed): prompt + W decode steps, then rewind to the end of the prompt ----
+    first = int(prompt().argmax())
+    model.decode_device(N_PROMPT, first, warmup, n_threads=args.threads)
+    first = int(prompt().argmax())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-resident loop, exactly `steps` steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    toks, _, ms = model.decode_device(N_PROMPT, first, steps, n_threads=args.threads)
+    sync_all()
+    clocks = sampler.summary()
+    launches = model.last_launches
+    t_value = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_value, op=dist.ReduceOp.MAX)
+    ms_value = float(t_value.item())
+
+    # ---- roofline: per-launch duration of the token kernel from CUDA events around every launch ----
+    first = int(prompt().argmax())
+    model.set_option("time_kernel", 1)
+    model.decode_device(N_PROMPT, first, steps, n_threads=args.threads)
+    kernel_ms = model.kernel_ms_total
+    model.set_option("time_kernel", 0)
+
+    # ---- e2e: the C-ABI llama_eval per token with host buffers ----
+    first = int(prompt().argmax())
+    cur = first
+    tok = np.empty(1, np.int32)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tok[0] = cur
+        logits = lsb.llama_eval(model, args.threads, N_PROMPT + i, tok)     # H2D token, kernels, D2H logits, sync
+        cur = int(logits.argmax())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e2e.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    tps = world * steps / (ms_value * 1e-3)
+    mean_bytes = float(np.mean([algorithmic_bytes(N_PROMPT + i) for i in range(steps)])) if args.layers == 32 else None
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+    roofline = None
+    if mean_bytes is not None and kernel_ms:
+        achieved = mean_bytes / (kernel_ms / steps * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "decode_token_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": mean_bytes, "weights_only_GBps": W_BYTES / (kernel_ms / steps * 1e-3) / 1e9,
+                    "kernel_us_per_launch": kernel_ms / steps * 1e3}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        ctps, n, desc = time_reference_cpu(path, 8, budget_s=25.0, max_steps=24)
+        if ctps is not None:
+            cpu = {"value": ctps, "unit": "tokens/s", "cores": 8, "kind": "reference", "sample": desc,
+                   "host_cores_available": os.cpu_count()}
+        else:
+            cpu = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": desc}
+
+    config.update({"parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (tensor-parallel sharding is not built yet)",
+                   "n_ctx": n_ctx, "graph": "CUDA graph replay of [memset, decode_token_kernel] + argmax kernel per step"})
+    line = {"metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_value / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int4 x int4 -> int32 block dots (dp4a), fp32 lane accumulation (bit-exact AVX2 order), f32 KV",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": world * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
+                    "note": "b200_llama_eval per token: token id by value, logits to pinned host memory, host arg-max"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    model.free()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,6 +72,9 @@ int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const 
  * quantized weights resident, and a knob to toggle CUDA-graph replay + programmatic dependent launch. */
 long long b200_llama_last_launches(const b200_llama *m);
 long long b200_llama_weight_bytes(const b200_llama *m);
+/* With option "time_kernel" = 1, b200_llama_decode_device brackets every token-kernel launch with CUDA events on the
+ * model's stream; this returns the sum of those per-launch durations (ms) for the last call. */
+double b200_llama_last_kernel_ms(const b200_llama *m);
 int b200_llama_set_option(b200_llama *m, const char *key, int value);
 
 /* Development profiler of the whole-token kernel: evaluates one token at position pos and returns per-CTA

@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     L.b200_llama_kv_import.restype = ci
     L.b200_llama_last_launches.argtypes, L.b200_llama_last_launches.restype = [vp], C.c_longlong
     L.b200_llama_weight_bytes.argtypes, L.b200_llama_weight_bytes.restype = [vp], C.c_longlong
+    L.b200_llama_last_kernel_ms.argtypes, L.b200_llama_last_kernel_ms.restype = [vp], C.c_double
     L.b200_llama_set_option.argtypes, L.b200_llama_set_option.restype = [vp, cp, ci], ci
     L.b200_q4_0_matvec.argtypes = [ci, vp, ci, ci, vp, vp, ci, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_0_matvec.restype = ci
@@ -110,6 +111,11 @@ class LlamaModel:
     @property
     def last_launches(self) -> int:
         return int(lib().b200_llama_last_launches(self._h))
+
+    @property
+    def kernel_ms_total(self) -> float:
+        """Sum of the per-launch token-kernel durations of the last decode_device call (option time_kernel = 1)."""
+        return float(lib().b200_llama_last_kernel_ms(self._h))
 
     @property
     def weight_bytes(self) -> int:

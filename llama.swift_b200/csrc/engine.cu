@@ -63,7 +63,7 @@ int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 24576) & ~127; }
+int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 32768) & ~127; }
 
 // Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
 GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
@@ -74,8 +74,7 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   p.g_total = Mpad / 4;
   p.n_cta = std::min(n_sm, p.g_total);
   p.rmax = 4 * ((p.g_total + p.n_cta - 1) / p.n_cta);
-  // as many threads per row as fit the 512 compute threads: the row loops are latency-bound, more warps hide more
-  int lp = p.rmax * 4 <= MEGA_COMPUTE_THREADS ? 1 : (p.rmax * 2 <= MEGA_COMPUTE_THREADS ? 2 : 4);
+  int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);   // measured best on B200 (profiles/r1_b_*)
   if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
   while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;
   p.lp = lp;
@@ -204,7 +203,9 @@ struct b200_llama {
   int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
   size_t mega_smem = 0;
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0, opt_time_kernel = 0;
+  double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
+  std::vector<cudaEvent_t> kev;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
 };
@@ -379,6 +380,7 @@ void free_model(b200_llama *m) {
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  for (cudaEvent_t e : m->kev) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -720,8 +722,13 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
   set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  if (m->opt_time_kernel) {
+    while ((int) m->kev.size() < 2 * n_steps) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); m->kev.push_back(e); }
+  }
   for (int i = 0; i < n_steps; i++) {
+    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
     CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
     if (logits_all) {
       CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
     }
@@ -732,6 +739,10 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
   CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, m->ev0, m->ev1));
+  if (m->opt_time_kernel) {
+    m->last_kernel_ms = 0.0;
+    for (int i = 0; i < n_steps; i++) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, m->kev[2 * i], m->kev[2 * i + 1])); m->last_kernel_ms += t; }
+  }
   if (tokens_out) CUDA_TRY(cudaMemcpy(tokens_out, m->d_token_log, (size_t) n_steps * 4, cudaMemcpyDeviceToHost));
   if (logits_all) CUDA_TRY(cudaMemcpy(logits_all, m->d_logits_log, (size_t) n_steps * m->n_vocab * 4, cudaMemcpyDeviceToHost));
   return B200_LLAMA_OK;
@@ -769,6 +780,7 @@ int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const 
 }
 
 long long b200_llama_last_launches(const b200_llama *m) { return m->last_launches; }
+double b200_llama_last_kernel_ms(const b200_llama *m) { return m->last_kernel_ms; }
 long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes; }
 
 /* Development profiler: run ONE token (current step scalars) through the whole-token kernel with per-CTA globaltimer
@@ -798,6 +810,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "graph")) { m->opt_graph = value; return 0; }
   if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
   if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
+  if (!strcmp(key, "time_kernel")) { m->opt_time_kernel = value; return 0; }
   if (!strcmp(key, "l2_ahead")) { m->opt_l2_ahead = value; if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; } return 0; }
   return -1;
 }

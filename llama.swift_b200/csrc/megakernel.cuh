@@ -312,8 +312,15 @@ __device__ __forceinline__ void group_compute(const GemvGroup<LP> &gr, u64 (&acc
   }
 }
 
+// Position in the ring of stages: stage index and the parity of its mbarrier phase, advanced without div/mod.
+struct RingPos {
+  int s;
+  uint32_t par;
+  __device__ __forceinline__ void next(int S) { if (++s == S) { s = 0; par ^= 1u; } }
+};
+
 template <int LP>
-__device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, uint32_t &gchunk,
+__device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                           int S, int stage_bytes, int tid) {
   constexpr int UPR = 4 / LP;
   const int R = rp.R, nb = md.nb, cb = md.cb;
@@ -329,9 +336,9 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
   const bool warp_active = (tid & ~31) < R * UPR;     // warps with no rows skip the math but still release stages
   const int wstride = R * 4;
 
-  for (int k = 0; k < nchunks; k++, gchunk++) {
-    const int s = gchunk % S;
-    mbar_wait(&sm.full[s], (gchunk / S) & 1);
+  for (int k = 0; k < nchunks; k++, ring.next(S)) {
+    const int s = ring.s;
+    mbar_wait(&sm.full[s], ring.par);
     if (warp_active) {
       const int cbk = min(cb, nb - k * cb);
       const uint8_t *st = sm.stages + (size_t) s * stage_bytes;
@@ -339,32 +346,6 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
       const float *sc = reinterpret_cast<const float *>(st + cbk * R * 16) + r;
       const uint4 *xqk = sm.xq + k * cb * 4 + pg * LP;
       const float *dxk = sm.dxs + k * cb;
-      if constexpr (LP == 1) {
-        // 3-4 resident warps per SM on the small-M matrices: nothing but ILP hides the LDS latency, so the operands of
-        // the next group of 4 blocks are fetched into a second register set while the current group is computed
-        constexpr int G = GemvGroup<LP>::G;
-        const int ngroups = cbk / G;
-        GemvGroup<LP> ga, gb;
-        if (ngroups > 0) group_load<LP>(ga, nib, sc, xqk, dxk, wstride, R);
-        int g = 0;
-        for (; g + 2 <= ngroups; g += 2) {
-          group_load<LP>(gb, nib + (g + 1) * G * wstride, sc + (g + 1) * G * R, xqk + (g + 1) * G * 4, dxk + (g + 1) * G, wstride, R);
-          group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
-          if (g + 2 < ngroups)
-            group_load<LP>(ga, nib + (g + 2) * G * wstride, sc + (g + 2) * G * R, xqk + (g + 2) * G * 4, dxk + (g + 2) * G, wstride, R);
-          group_compute<LP>(gb, acc, cvt_mul, cvt_sub);
-        }
-        if (g < ngroups) group_compute<LP>(ga, acc, cvt_mul, cvt_sub);
-        for (int bl = ngroups * G; bl < cbk; bl++) {   // leftover blocks
-          const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);
-          const uint32_t wv = nib[bl * wstride];
-          const uint4 xv = xqk[bl * 4];
-          const int ia = dp4a_us(wv & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
-          const int ib = dp4a_us(wv & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
-          const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
-          acc[0] = ffma2(pack_f2(sdx, sdx), f, acc[0]);
-        }
-      } else {
 #pragma unroll 4
       for (int bl = 0; bl < cbk; bl++) {
         uint32_t wv[LP];
@@ -387,7 +368,6 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
           acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                           // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
         }
       }
-          }
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
@@ -418,25 +398,27 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
-__device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, uint32_t &gchunk,
+__device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                               int S, int stage_bytes, int tid) {
   if (rp.R == 0) { named_bar_sync(1, MEGA_COMPUTE_THREADS); return; }
   switch (md.lp) {
-    case 1: gemv_rows<1>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
-    case 2: gemv_rows<2>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
-    default: gemv_rows<4>(md, rp, sm, gchunk, S, stage_bytes, tid); break;
+    case 1: gemv_rows<1>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    case 2: gemv_rows<2>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    default: gemv_rows<4>(md, rp, sm, ring, S, stage_bytes, tid); break;
   }
 }
 
 // loader side of one matrix: ring stages <- this CTA's contiguous bytes, one cp.async.bulk per chunk
-__device__ __forceinline__ void stream_matrix(const MatDesc &md, const MegaSmem &sm, uint32_t &gchunk, int S, int stage_bytes) {
+__device__ __forceinline__ void stream_matrix(const MatDesc &md, const MegaSmem &sm, RingPos &ring, int S, int stage_bytes) {
   const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
   if (rp.R == 0) return;
   const int nchunks = (md.nb + md.cb - 1) / md.cb;
   const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
-  for (int k = 0; k < nchunks; k++, gchunk++) {
-    const int s = gchunk % S;
-    if (gchunk >= (uint32_t) S) mbar_wait(&sm.empty[s], ((gchunk / S) - 1) & 1);
+  for (int k = 0; k < nchunks; k++, ring.next(S)) {
+    const int s = ring.s;
+    // ring.par is the parity of the fill about to start; the slot is free once the consumers released the previous
+    // fill (parity par ^ 1).  On a fresh barrier that wait returns at once (the first lap needs no release).
+    mbar_wait(&sm.empty[s], ring.par ^ 1u);
     const int cbk = min(md.cb, md.nb - k * md.cb);
     const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
     mbar_arrive_expect_tx(&sm.full[s], bytes);
@@ -583,7 +565,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   if (tid >= MEGA_COMPUTE_THREADS) {
     if (tid == MEGA_COMPUTE_THREADS) {
       // ===== TMA loader: the whole token's weight stream for this SM, in schedule order =====
-      uint32_t g = 0;
+      RingPos g = {0, 0u};
       for (int il = 0; il < a.n_layer; il++) {
         stream_matrix(a.layers[il].qkv, sm, g, S, stage_bytes);
         stream_matrix(a.layers[il].wo, sm, g, S, stage_bytes);
@@ -601,7 +583,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // mat-vec).  Descriptors come from the kernel parameter block (constant bank).
   const int E = a.n_embd, HD = E / a.n_head;
   const int pos = a.sp->pos;
-  uint32_t gchunk = 0;
+  RingPos gchunk = {0, 0u};
   unsigned int phase = 0;
   int pm = 0;
   PROF_MARK();   // 0: kernel start
