@@ -210,11 +210,10 @@ def main():
     model.decode_device(N_PROMPT, first, warmup, n_threads=args.threads)
     first = int(prompt().argmax())
 
+    from llama_swift_b200 import dist_util
+
     def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+        dist_util.barrier_and_sync(torch.cuda.synchronize)
 
     # ---- value: device-resident loop, exactly `steps` steps ----
     sampler = ClockSampler(local_rank)
@@ -224,10 +223,7 @@ def main():
     sync_all()
     clocks = sampler.summary()
     launches = model.last_launches
-    t_value = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_value, op=dist.ReduceOp.MAX)
-    ms_value = float(t_value.item())
+    ms_value = dist_util.max_over_ranks(ms, "cuda")
 
     # ---- roofline: per-launch duration of the token kernel from CUDA events around every launch ----
     first = int(prompt().argmax())
@@ -248,10 +244,7 @@ def main():
         cur = int(logits.argmax())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
+    e2e_s = dist_util.max_over_ranks(e2e_s, "cuda")
 
     if rank != 0:
         if dist is not None:

@@ -164,3 +164,23 @@ def test_error_behaviour(tmp_path, small_model):
         assert gpu.id_to_token(5) == b" t5" and gpu.id_to_token(0) == b""
     finally:
         gpu.free()
+
+
+@pytest.mark.parametrize("nth", [1, 8])
+def test_llama_eval_vs_golden_reference_vectors(nth):
+    """The CUDA path against the committed outputs of the UNMODIFIED reference (tests/golden/reference_vectors.npz)."""
+    from conftest import ROOT
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    gpu = lsb.llama_model_load(model_file(n_layer=1, n_vocab=256, seed=11), n_ctx=16)
+    try:
+        toks, n_past = G["eval_tokens"], 0
+        for i, n in enumerate((4, 1, 1)):
+            got = lsb.llama_eval(gpu, nth, n_past, toks[n_past:n_past + n])
+            want = G[f"eval_logits_nth{nth}_{i}"]
+            assert rel_l2(got, want) <= 1e-3 and got.argmax() == want.argmax()
+            assert np.array_equal(bits(got), bits(want)), "expected bit-identical logits vs the reference CPU run"
+            n_past += n
+        assert np.array_equal(bits(gpu.kv_export(0, 0, n_past)[:, :256]), bits(G[f"eval_k0_nth{nth}"]))
+        assert np.array_equal(bits(gpu.kv_export(0, 1, n_past)[:, :256]), bits(G[f"eval_v0_nth{nth}"]))
+    finally:
+        gpu.free()
