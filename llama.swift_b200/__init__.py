@@ -20,7 +20,7 @@ import numpy as np
 from . import ggml_format  # noqa: F401  (writer for the reference's model file format)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200llama.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200llama.so")   # B200_LIB: development A/B builds
 
 ERR_LOAD = -1000      # LlamaErrorCodeFailedToLoadModel, headers/LlamaError.h:17
 ERR_PREDICT = -1001   # LlamaErrorCodePredictionFailed,  headers/LlamaError.h:18

@@ -22,8 +22,10 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in SRCS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB) -> str:
+    """defs/out: development A/B builds (e.g. defs=["-DB200_ROWLOOP=0"], out=.../libb200llama_r0.so, picked up through
+    the B200_LIB environment variable); the product is the default build."""
+    if not force and not defs and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     obj_host = os.path.join(HERE, "csrc", "host_math.o")
@@ -33,12 +35,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false",                       # FMAs only where the reference has them (explicit fmaf / fma.rn.f32x2)
            "-Xcompiler", "-fPIC", "-shared", "-ccbin", "g++",
-           os.path.join(HERE, "csrc", "engine.cu"), obj_host, "-o", LIB, "-lcudart"]
+           os.path.join(HERE, "csrc", "engine.cu"), obj_host, "-o", out, "-lcudart"] + list(defs)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=defs, out=outs[0] if outs else LIB))

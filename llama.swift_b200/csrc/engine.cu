@@ -81,6 +81,8 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
   // one ring-stage holds one chunk in both the per-matrix kernels and the whole-token kernel
   p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 20)));
+  const int batch = lp == 1 ? 8 : (lp == 2 ? 4 : 2);     // blocks whose loads the row loop issues together
+  if (p.cb >= batch) p.cb -= p.cb % batch;
   p.stage_bytes = (p.cb * p.rmax * 20 + 127) & ~127;
   const int nchunks = (p.nb + p.cb - 1) / p.cb;
   const size_t fixed = (size_t) p.nb * 64 + (size_t) ((p.nb + 3) & ~3) * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
@@ -634,13 +636,13 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
     const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
-                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 16;
+                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
-    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS;
+    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
     auto rows_fit = [&](const GemvPlan &p) { return p.rmax * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
     fits = fits && rows_fit(m->out);
     for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);

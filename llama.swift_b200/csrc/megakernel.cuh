@@ -110,7 +110,7 @@ struct MegaSmem {
   float *redf;      // [2][16]
   float *part;      // [MEGA_MAX_NTH][32]
   uint64_t *full, *empty;
-  volatile uint32_t *loader_g;   // loader progress, read by the prefetch warp
+  volatile uint32_t *done;       // [MEGA_COMPUTE_WARPS] chunks of the token each compute warp has finished with
 };
 
 // Block-wide sums over the compute warps with ONE barrier: warp shuffle tree, 14 partials, then every warp folds the
@@ -180,17 +180,35 @@ __device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s
 
 // ---- activation prologues ------------------------------------------------------------------------------------------
 // PLAIN: quantize x[K] (global, read through L2) -> xq/dxs.  An "item" is 8 consecutive floats = a quarter block.
+template <int ROUNDS>
+__device__ __forceinline__ void prologue_plain_r(const float *x, int items, const MegaSmem &sm, int tid) {
+  float4 va[ROUNDS], vc[ROUNDS];
+#pragma unroll
+  for (int rd = 0; rd < ROUNDS; rd++) {   // every round's loads are in flight before the first quantize: one L2 latency
+    const int it = min(tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    va[rd] = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2);
+    vc[rd] = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2 + 1);
+  }
+#pragma unroll
+  for (int rd = 0; rd < ROUNDS; rd++) {
+    const int it = tid + rd * MEGA_COMPUTE_THREADS;
+    const bool live = it < items;         // a block's 4 quarter-items are all live or all padding (512 % 4 == 0)
+    const int iq = live ? it : items - 1;
+    const float v[8] = {va[rd].x, va[rd].y, va[rd].z, va[rd].w, vc[rd].x, vc[rd].y, vc[rd].z, vc[rd].w};
+    quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+  }
+}
+
 __device__ __forceinline__ void prologue_plain(const float *x, int nb, const MegaSmem &sm, int tid) {
   const int items = nb * 4;
   const int rounds = (items + MEGA_COMPUTE_THREADS - 1) / MEGA_COMPUTE_THREADS;
-  for (int rd = 0; rd < rounds; rd++) {
-    const int it = tid + rd * MEGA_COMPUTE_THREADS;
-    const bool live = it < items;       // a block's 4 quarter-items are all live or all padding (448 % 4 == 0)
-    const int iq = live ? it : items - 1;
-    const float4 a = __ldcg(reinterpret_cast<const float4 *>(x) + iq * 2);
-    const float4 c = __ldcg(reinterpret_cast<const float4 *>(x) + iq * 2 + 1);
-    const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-    quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+  switch (rounds) {
+    case 1: prologue_plain_r<1>(x, items, sm, tid); break;
+    case 2: prologue_plain_r<2>(x, items, sm, tid); break;
+    case 3: prologue_plain_r<3>(x, items, sm, tid); break;
+    case 4: prologue_plain_r<4>(x, items, sm, tid); break;
+    case 5: prologue_plain_r<5>(x, items, sm, tid); break;
+    default: prologue_plain_r<6>(x, items, sm, tid); break;   // K <= 24576 (the host refuses larger n_ff for this kernel)
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
@@ -261,62 +279,24 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 }
 
 // ---- GEMV main loop over this CTA's rows of one matrix; leaves the row results in sm.rowres -------------------------
-// One "group" = G blocks of this thread's LP lane-pairs.  The loop is software pipelined by hand: the shared-memory
-// operands of group g+1 are loaded into a second register set while group g is computed, because with 1-2 resident
-// warps per scheduler (small-M matrices) nothing else hides the LDS latency.
-template <int LP>
-struct GemvGroup {
-  static constexpr int G = 4;   // blocks per software-pipeline group (used by the LP = 1 row loop)
-  uint32_t w[G * LP];     // [g][j] -> w[g * LP + j]
-  uint4 x[G * LP];
-  float sc[G], dx[G];
-};
-
-template <int LP>
-__device__ __forceinline__ void group_load(GemvGroup<LP> &gr, const uint32_t *nib, const float *sc, const uint4 *xq,
-                                           const float *dx, int wstride /*words per block*/, int sstride) {
-  constexpr int G = GemvGroup<LP>::G;
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    if constexpr (LP == 4) {
-      const uint4 t = *reinterpret_cast<const uint4 *>(nib + g * wstride);
-      gr.w[0] = t.x; gr.w[1] = t.y; gr.w[2] = t.z; gr.w[3] = t.w;
-    } else if constexpr (LP == 2) {
-      const uint2 t = *reinterpret_cast<const uint2 *>(nib + g * wstride);
-      gr.w[g * 2] = t.x; gr.w[g * 2 + 1] = t.y;
-    } else {
-      gr.w[g] = nib[g * wstride];
-    }
-    gr.sc[g] = sc[g * sstride];
-    gr.dx[g] = dx[g];
-#pragma unroll
-    for (int j = 0; j < LP; j++) gr.x[g * LP + j] = xq[g * 4 + j];
-  }
-}
-
-template <int LP>
-__device__ __forceinline__ void group_compute(const GemvGroup<LP> &gr, u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
-  constexpr int G = GemvGroup<LP>::G;
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    const float sdx = __fmul_rn(gr.sc[g], gr.dx[g]);                              // _mm256_mul_ps(d0, d1), ggml.c:1431
-#pragma unroll
-    for (int j = 0; j < LP; j++) {
-      const uint32_t wv = gr.w[g * LP + j];
-      const uint4 xv = gr.x[g * LP + j];
-      const int ia = dp4a_us(wv & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);          // float bits of 12582912 + isum(lane 2p)
-      const int ib = dp4a_us(wv & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);          // float bits of 12582912 + 16*isum(lane 2p+1)
-      const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                     // exact (float)isum for both lanes
-      acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                               // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
-    }
-  }
-}
+// Both alternatives were measured on B200 (7B, 64 decode steps): ROWLOOP/DONE_FLAGS = 0/0 1664 us/token, 1/0 1685,
+// 0/1 1747, 1/1 1713 -- the plain loop and the mbarrier ring win; the others stay selectable for A/B builds.
+#ifndef B200_ROWLOOP
+#define B200_ROWLOOP 0      // 1: loads of U blocks batched ahead of their math; 0: unroll 4, ptxas schedules
+#endif
+#ifndef B200_DONE_FLAGS
+#define B200_DONE_FLAGS 0   // 1: stage release through per-warp progress words (idle warps sleep); 0: mbarrier ring
+#endif
+#ifndef B200_NO_MATH
+#define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
+#endif
 
 // Position in the ring of stages: stage index and the parity of its mbarrier phase, advanced without div/mod.
 struct RingPos {
   int s;
   uint32_t par;
-  __device__ __forceinline__ void next(int S) { if (++s == S) { s = 0; par ^= 1u; } }
+  uint32_t g;      // chunks consumed / issued so far (global index of the next one)
+  __device__ __forceinline__ void next(int S) { g++; if (++s == S) { s = 0; par ^= 1u; } }
 };
 
 template <int LP>
@@ -336,41 +316,91 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
   const bool warp_active = (tid & ~31) < R * UPR;     // warps with no rows skip the math but still release stages
   const int wstride = R * 4;
 
+#if B200_DONE_FLAGS
+  if (!warp_active) {
+    // this warp owns no rows of this matrix: mark its share of the ring as consumed and go to sleep in the barrier
+    for (int k = 0; k < nchunks; k++) ring.next(S);
+    if ((tid & 31) == 0) sm.done[tid >> 5] = ring.g;
+  } else
+#endif
   for (int k = 0; k < nchunks; k++, ring.next(S)) {
     const int s = ring.s;
     mbar_wait(&sm.full[s], ring.par);
-    if (warp_active) {
+    if (warp_active && !B200_NO_MATH) {
       const int cbk = min(cb, nb - k * cb);
       const uint8_t *st = sm.stages + (size_t) s * stage_bytes;
-      const uint32_t *nib = reinterpret_cast<const uint32_t *>(st) + r * 4 + pg * LP;
-      const float *sc = reinterpret_cast<const float *>(st + cbk * R * 16) + r;
-      const uint4 *xqk = sm.xq + k * cb * 4 + pg * LP;
-      const float *dxk = sm.dxs + k * cb;
+      const uint32_t *pw = reinterpret_cast<const uint32_t *>(st) + r * 4 + pg * LP;
+      const float *ps = reinterpret_cast<const float *>(st + cbk * R * 16) + r;
+      const uint4 *px = sm.xq + k * cb * 4 + pg * LP;
+      const float *pd = sm.dxs + k * cb;
+      int bl = 0;
+#if B200_ROWLOOP
+      constexpr int U = LP == 1 ? 8 : (LP == 2 ? 4 : 2);
+      for (; bl + U <= cbk; bl += U) {
+        uint32_t wv[U][LP];
+        uint4 xv[U][LP];
+        float scv[U], dxv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if constexpr (LP == 4) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(pw + u * wstride);
+            wv[u][0] = t.x; wv[u][1] = t.y; wv[u][2] = t.z; wv[u][3] = t.w;
+          } else if constexpr (LP == 2) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(pw + u * wstride);
+            wv[u][0] = t.x; wv[u][1] = t.y;
+          } else {
+            wv[u][0] = pw[u * wstride];
+          }
+          scv[u] = ps[u * R];
+          dxv[u] = pd[u];
+#pragma unroll
+          for (int j = 0; j < LP; j++) xv[u][j] = px[u * 4 + j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const float sdx = __fmul_rn(scv[u], dxv[u]);                           // _mm256_mul_ps(d0, d1), ggml.c:1431
+#pragma unroll
+          for (int j = 0; j < LP; j++) {
+            const int ia = dp4a_us(wv[u][j] & 0x0F0F0F0Fu, (int) xv[u][j].x, (int) xv[u][j].z);   // float bits of 12582912 + isum(lane 2p)
+            const int ib = dp4a_us(wv[u][j] & 0xF0F0F0F0u, (int) xv[u][j].y, (int) xv[u][j].w);   // float bits of 12582912 + 16*isum(lane 2p+1)
+            const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);               // exact (float)isum for both lanes
+            acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                         // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+          }
+        }
+        pw += U * wstride; ps += U * R; px += U * 4; pd += U;
+      }
+#else
 #pragma unroll 4
-      for (int bl = 0; bl < cbk; bl++) {
+#endif
+      for (; bl < cbk; bl++) {
         uint32_t wv[LP];
         if constexpr (LP == 4) {
-          const uint4 t = *reinterpret_cast<const uint4 *>(nib + bl * wstride);
+          const uint4 t = *reinterpret_cast<const uint4 *>(pw);
           wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
         } else if constexpr (LP == 2) {
-          const uint2 t = *reinterpret_cast<const uint2 *>(nib + bl * wstride);
+          const uint2 t = *reinterpret_cast<const uint2 *>(pw);
           wv[0] = t.x; wv[1] = t.y;
         } else {
-          wv[0] = nib[bl * wstride];
+          wv[0] = pw[0];
         }
-        const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);                        // _mm256_mul_ps(d0, d1), ggml.c:1431
+        const float sdx = __fmul_rn(ps[0], pd[0]);
 #pragma unroll
         for (int j = 0; j < LP; j++) {
-          const uint4 xv = xqk[bl * 4 + j];
-          const int ia = dp4a_us(wv[j] & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);   // float bits of 12582912 + isum(lane 2p)
-          const int ib = dp4a_us(wv[j] & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);   // float bits of 12582912 + 16*isum(lane 2p+1)
-          const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                 // exact (float)isum for both lanes
-          acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                           // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+          const uint4 xv = px[j];
+          const int ia = dp4a_us(wv[j] & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
+          const int ib = dp4a_us(wv[j] & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
+          const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
+          acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);
         }
+        pw += wstride; ps += R; px += 4; pd += 1;
       }
     }
     __syncwarp();
+#if B200_DONE_FLAGS
+    if ((tid & 31) == 0) sm.done[tid >> 5] = ring.g + 1;      // chunk ring.g of the token is consumed by this warp
+#else
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+#endif
   }
 
   // horizontal sum exactly as ggml.c:1461-1466: (acc[k]+acc[k+4]) k<4, then (r0+r2)+(r1+r3)
@@ -408,45 +438,6 @@ __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart r
   }
 }
 
-// loader side of one matrix: ring stages <- this CTA's contiguous bytes, one cp.async.bulk per chunk
-__device__ __forceinline__ void stream_matrix(const MatDesc &md, const MegaSmem &sm, RingPos &ring, int S, int stage_bytes) {
-  const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
-  if (rp.R == 0) return;
-  const int nchunks = (md.nb + md.cb - 1) / md.cb;
-  const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
-  for (int k = 0; k < nchunks; k++, ring.next(S)) {
-    const int s = ring.s;
-    // ring.par is the parity of the fill about to start; the slot is free once the consumers released the previous
-    // fill (parity par ^ 1).  On a fresh barrier that wait returns at once (the first lap needs no release).
-    mbar_wait(&sm.empty[s], ring.par ^ 1u);
-    const int cbk = min(md.cb, md.nb - k * md.cb);
-    const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
-    mbar_arrive_expect_tx(&sm.full[s], bytes);
-    tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
-  }
-}
-
-// prefetch side of one matrix: keep the stream [loader + S, loader + S + ahead) resident in L2
-__device__ __forceinline__ void prefetch_matrix(const MatDesc &md, const MegaSmem &sm, uint32_t &pchunk, int S, int ahead) {
-  const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
-  if (rp.R == 0) return;
-  const int nchunks = (md.nb + md.cb - 1) / md.cb;
-  const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
-  for (int k = 0; k < nchunks; k++, pchunk++) {
-    uint32_t lg = *sm.loader_g;
-    if (pchunk < lg + (uint32_t) S) continue;                 // the loader is (nearly) there already: nothing to gain
-    if (pchunk >= lg + (uint32_t) (S + ahead)) {
-      const long long t0 = clock64();
-      while (pchunk >= (lg = *sm.loader_g) + (uint32_t) (S + ahead)) {
-        __nanosleep(256);
-        if (clock64() - t0 > 4000000000LL) return;            // loader gone (should not happen): stop prefetching
-      }
-    }
-    const int cbk = min(md.cb, md.nb - k * md.cb);
-    l2_prefetch_bulk(wbase + (size_t) k * md.cb * rp.R * 20, (uint32_t) cbk * rp.R * 20);
-  }
-}
-
 // ---- attention phase for (head h, output quarter qr): K.Q for all positions, soft_max, V.P for 32 dims --------------
 __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerDesc &L, const MegaSmem &sm, int h, int qr,
                                                 int pos, int p_part, int tid) {
@@ -459,17 +450,18 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
 #pragma unroll
   for (int i = 0; i < 4; i++) qv[i] = __ldcg(a.q + h * HD + lane + 32 * i);
   // K.Q: ggml_vec_dot_f32, AVX mapping (lane t = 8*vec + l owns elements t, t+32, t+64, t+96), ggml.c:1223-1258, 872-887
-  for (int j0 = warp * 4; j0 < p_valid; j0 += NW * 4) {
-    float kk[4][4];
+  constexpr int KB = 8;     // positions per batch: 32 independent loads in flight per lane
+  for (int j0 = warp * KB; j0 < p_valid; j0 += NW * KB) {
+    float kk[KB][4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < KB; u++) {
       const int j = min(j0 + u, p_valid - 1);
       const float *kp = L.k_layer + (size_t) j * E + h * HD + lane;
 #pragma unroll
       for (int i = 0; i < 4; i++) kk[u][i] = __ldcg(kp + 32 * i);
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < KB; u++) {
       float s = 0.0f;
 #pragma unroll
       for (int i = 0; i < 4; i++) s = fmaf(kk[u][i], qv[i], s);                  // GGML_F32_VEC_FMA, ggml.c:1239
@@ -507,12 +499,28 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     const int j1 = min(min(j0 + dc, p_part), p_valid);
     float acc = 0.0f;
     int j = j0;
-    for (; j + 8 <= j1; j += 8) {
+    for (; j + 16 <= j1; j += 16) {
+      float vv[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc = fmaf(vv[i], sc[j + i], acc);           // vec_mad_f32, ggml.c:1696
+    }
+    if (j + 8 <= j1) {
       float vv[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
 #pragma unroll
-      for (int i = 0; i < 8; i++) acc = fmaf(vv[i], sc[j + i], acc);            // vec_mad_f32, ggml.c:1696
+      for (int i = 0; i < 8; i++) acc = fmaf(vv[i], sc[j + i], acc);
+      j += 8;
+    }
+    if (j + 4 <= j1) {
+      float vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
+#pragma unroll
+      for (int i = 0; i < 4; i++) acc = fmaf(vv[i], sc[j + i], acc);
+      j += 4;
     }
     for (; j < j1; j++) acc = fmaf(__ldcg(vp + (size_t) j * E), sc[j], acc);
     sm.part[t * 32 + lane] = acc;
@@ -541,7 +549,7 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   sm.part = sm.redf + 32;
   sm.full = reinterpret_cast<uint64_t *>(sm.part + MEGA_MAX_NTH * 32);
   sm.empty = sm.full + S;
-  sm.loader_g = reinterpret_cast<volatile uint32_t *>(sm.empty + S);
+  sm.done = reinterpret_cast<volatile uint32_t *>(sm.empty + S);
   return sm;
 }
 
@@ -557,22 +565,71 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], MEGA_COMPUTE_WARPS); }
-    *sm.loader_g = 0;
+    for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) sm.done[w] = 0;
     fence_mbar_init();
   }
   __syncthreads();
 
   if (tid >= MEGA_COMPUTE_THREADS) {
     if (tid == MEGA_COMPUTE_THREADS) {
-      // ===== TMA loader: the whole token's weight stream for this SM, in schedule order =====
-      RingPos g = {0, 0u};
-      for (int il = 0; il < a.n_layer; il++) {
-        stream_matrix(a.layers[il].qkv, sm, g, S, stage_bytes);
-        stream_matrix(a.layers[il].wo, sm, g, S, stage_bytes);
-        stream_matrix(a.layers[il].w13, sm, g, S, stage_bytes);
-        stream_matrix(a.layers[il].w2, sm, g, S, stage_bytes);
+      // ===== TMA loader: the whole token's weight stream for this SM, in schedule order.  With l2_ahead > 0 a second
+      // cursor runs that many chunks further down the same schedule and pulls them from HBM into L2
+      // (cp.async.bulk.prefetch.L2) so that HBM keeps streaming while the ring is full =====
+      RingPos g = {0, 0u, 0u};
+      uint32_t done_min = 0;
+      const int n_mats = 4 * a.n_layer + 1;
+      int pm_idx = 0, pk = 0;            // prefetch cursor: matrix index in the schedule, chunk within it
+      uint32_t pg = 0;                   // global index of the next chunk to prefetch
+      for (int mi = 0; mi < n_mats; mi++) {
+        const MatDesc &md = mi < 4 * a.n_layer ? (&a.layers[mi >> 2].qkv)[mi & 3] : a.out;
+        const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
+        if (rp.R == 0) continue;
+        const int nchunks = (md.nb + md.cb - 1) / md.cb;
+        const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
+        for (int k = 0; k < nchunks; k++, g.next(S)) {
+          const int s = g.s;
+#if B200_DONE_FLAGS
+          if (g.g >= (uint32_t) S) {
+            const uint32_t need = g.g - (uint32_t) S + 1u;
+            if (done_min < need) {
+              const long long t0 = clock64();
+              for (;;) {
+                uint32_t mn = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) mn = min(mn, sm.done[w]);
+                done_min = mn;
+                if (mn >= need) break;
+                if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+          }
+#else
+          // g.par is the parity of the fill about to start; the slot is free once the consumers released the previous
+          // fill (parity par ^ 1).  On a fresh barrier that wait returns at once (the first lap needs no release).
+          mbar_wait(&sm.empty[s], g.par ^ 1u);
+#endif
+          const int cbk = min(md.cb, md.nb - k * md.cb);
+          const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
+          mbar_arrive_expect_tx(&sm.full[s], bytes);
+          tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
+          if (a.l2_ahead > 0) {
+            // keep chunks (g.g + S, g.g + S + l2_ahead] of the stream on their way into L2
+            const uint32_t lo = g.g + 1u + (uint32_t) S, hi = lo + (uint32_t) a.l2_ahead;
+            while (pm_idx < n_mats && pg < hi) {
+              const MatDesc &pd = pm_idx < 4 * a.n_layer ? (&a.layers[pm_idx >> 2].qkv)[pm_idx & 3] : a.out;
+              const RowPart pr = row_part(pd.g_total, gridDim.x, blockIdx.x);
+              const int pn = pr.R == 0 ? 0 : (pd.nb + pd.cb - 1) / pd.cb;
+              if (pk >= pn) { pm_idx++; pk = 0; continue; }
+              if (pg >= lo) {
+                const int pc = min(pd.cb, pd.nb - pk * pd.cb);
+                l2_prefetch_bulk(pd.w + (size_t) pr.row0 * pd.nb * 20 + (size_t) pk * pd.cb * pr.R * 20, (uint32_t) pc * pr.R * 20);
+              }
+              pk++; pg++;
+            }
+          }
+        }
       }
-      stream_matrix(a.out, sm, g, S, stage_bytes);
     }
     return;
   }
@@ -583,7 +640,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // mat-vec).  Descriptors come from the kernel parameter block (constant bank).
   const int E = a.n_embd, HD = E / a.n_head;
   const int pos = a.sp->pos;
-  RingPos gchunk = {0, 0u};
+  RingPos gchunk = {0, 0u, 0u};
   unsigned int phase = 0;
   int pm = 0;
   PROF_MARK();   // 0: kernel start
