@@ -52,6 +52,7 @@ void set_err(char *err, size_t errlen, const char *fmt, ...) {
   } while (0)
 
 struct GemvPlan {
+  int split = 0;            // whole-token kernel runs this matrix in producer/chain mode
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
   int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
@@ -83,6 +84,11 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 20)));
   const int batch = lp == 1 ? 8 : (lp == 2 ? 4 : 2);     // blocks whose loads the row loop issues together
   if (p.cb >= batch) p.cb -= p.cb % batch;
+  // small matrices: producer/chain row loop of the whole-token kernel (hands over SPLIT_SB blocks at a time)
+  if (env_int("B200_SPLIT", 1) && p.rmax * 4 <= 128 && p.nb % SPLIT_SB == 0 && p.cb >= SPLIT_SB) {
+    p.split = 1;
+    p.cb -= p.cb % SPLIT_SB;
+  }
   p.stage_bytes = (p.cb * p.rmax * 20 + 127) & ~127;
   const int nchunks = (p.nb + p.cb - 1) / p.cb;
   const size_t fixed = (size_t) p.nb * 64 + (size_t) ((p.nb + 3) & ~3) * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
@@ -202,7 +208,7 @@ struct b200_llama {
   int prof_marks = 0;
   TokenArgs *h_token_args = nullptr;   // host copy of the kernel parameter block (layer descriptors prefilled)
   unsigned int *d_bar = nullptr;
-  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
+  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0, mega_split_rows = 0;
   size_t mega_smem = 0;
 
   int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0, opt_time_kernel = 0;
@@ -221,7 +227,7 @@ int attn_smem_bytes(const b200_llama *m, int n_threads) {
 // One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
 MatDesc mat_desc(const GemvPlan &p) {
   MatDesc d = {};
-  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp;
+  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.pad = p.split;
   return d;
 }
 
@@ -240,6 +246,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
+  a.split_rows = m->mega_split_rows;
   a.prof = m->d_prof; a.prof_marks = m->prof_marks;
   a.l2_ahead = m->opt_l2_ahead;
   cudaLaunchConfig_t cfg = {};
@@ -623,6 +630,7 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     for (int i = 0; i < m->n_layer; i++) {
       descs[i].qkv = mat_desc(m->layers[i].qkv); descs[i].wo = mat_desc(m->layers[i].wo);
       descs[i].w13 = mat_desc(m->layers[i].w13); descs[i].w2 = mat_desc(m->layers[i].w2);
+      descs[i].qkv.pad = 0; descs[i].w13.pad = 0;      // producer/chain mode is for the small matrices (wo, w2) only
       descs[i].attn_norm = m->layers[i].attn_norm; descs[i].ffn_norm = m->layers[i].ffn_norm;
       descs[i].k_layer = m->d_k + (size_t) i * n_ctx * E; descs[i].v_layer = m->d_v + (size_t) i * n_ctx * E;
     }
@@ -635,7 +643,14 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     const int nb_max = std::max(E, F) / 32;
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
-    const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
+    for (auto &L : m->layers) {
+      if (L.wo.split) m->mega_split_rows = std::max(m->mega_split_rows, L.wo.rmax);
+      if (L.w2.split) m->mega_split_rows = std::max(m->mega_split_rows, L.w2.rmax);
+      L.qkv.split = 0; L.w13.split = 0;
+    }
+    m->out.split = 0;
+    const size_t fixed = (size_t) 2 * SPLIT_SB * m->mega_split_rows * 36 +
+                         (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
                          MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;

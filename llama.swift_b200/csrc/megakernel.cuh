@@ -26,7 +26,7 @@ struct MatDesc {
   int nb;             // blocks per row
   int cb;             // blocks per chunk
   int lp;             // lane-pairs per thread (1, 2 or 4)
-  int pad;
+  int pad;            // != 0: run this matrix in producer/chain mode (gemv_rows_split)
 };
 
 struct LayerDesc {
@@ -52,6 +52,7 @@ struct TokenArgs {
   float kq_scale;
   int S, stage_bytes;
   int xs_floats;            // size of the f32 scratch area (attention scores): >= n_ctx
+  int split_rows;           // rows per CTA of the largest matrix run in producer/chain mode (0: mode off)
   int l2_ahead;             // chunks the L2-prefetch warp may run ahead of the loader (0 = off)
   long long *prof;          // optional [gridDim.x][prof_marks] globaltimer stamps (development profiler), else null
   int prof_marks;
@@ -61,6 +62,7 @@ constexpr int MEGA_COMPUTE_WARPS = 16;
 constexpr int MEGA_COMPUTE_THREADS = MEGA_COMPUTE_WARPS * 32;   // 512: one 8-float item per thread at n_embd 4096
 constexpr int MEGA_THREADS = MEGA_COMPUTE_THREADS + 32;          // + the TMA loader warp (96 regs/thread)
 constexpr int MEGA_MAX_ROWS = 512;     // rows per CTA upper bound (rowres[])
+constexpr int SPLIT_SB = 16;          // blocks per producer/chain hand-over in the small-matrix row loop
 constexpr int MEGA_MAX_NTH = 16;       // reference thread counts supported by the V*P partition
 constexpr int MEGA_NORM_ROUNDS = 2;    // 8-element items per thread held in registers by the LayerNorm prologue (K <= 7168)
 
@@ -109,6 +111,8 @@ struct MegaSmem {
   double *redd;     // [2][16]
   float *redf;      // [2][16]
   float *part;      // [MEGA_MAX_NTH][32]
+  float2 *splitF;   // [2][SPLIT_SB][split_rows][4]  exact (float)isum pairs, producer warps -> chain warps
+  float *splitS;    // [2][SPLIT_SB][split_rows]     d_w*d_x per (block,row)
   uint64_t *full, *empty;
   volatile uint32_t *done;       // [MEGA_COMPUTE_WARPS] chunks of the token each compute warp has finished with
 };
@@ -428,9 +432,104 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
+// ---- small matrices (R*4 <= 128 threads: wo, w2): producer/chain split -------------------------------------------------
+// With 28 rows per CTA only 112 threads own an accumulator chain, and the chain itself is just one FMA per block
+// (acc = fma(d_w*d_x, (float)isum, acc), strictly sequential in the reference).  Everything in front of that FMA --
+// nibble unpack, dp4a, exact int->float, the scale product -- is independent per (row, block, lane pair), so the 12
+// warps that own no chain compute it for SPLIT_SB blocks at a time into a double-buffered staging area and the 4
+// chain warps only do LDS + FFMA2.  Same operations, same order per lane: bit-identical to the one-thread-per-chain loop.
+__device__ __forceinline__ void gemv_rows_split(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
+                                                int S, int stage_bytes, int split_rows, int tid) {
+  constexpr int NCHAIN = 128;                                    // chain threads (warps 0-3): tid = 4*row + pair
+  constexpr int NPROD = MEGA_COMPUTE_THREADS - NCHAIN;           // producer threads (warps 4-15)
+  constexpr int MAXI = 6;                                        // producer items per hand-over, SPLIT_SB*32*4 / NPROD rounded up
+  const int R = rp.R, nb = md.nb, cb = md.cb;
+  const int R4 = R * 4;
+  const int subs_per_chunk = cb / SPLIT_SB;                      // host guarantees cb % SPLIT_SB == 0 and nb % SPLIT_SB == 0
+  const int nsub = nb / SPLIT_SB;
+  const bool is_chain = tid < NCHAIN;
+  const bool chain_active = tid < R4;
+  const int cr = chain_active ? tid >> 2 : R - 1, cp = tid & 3;
+  // producer: the items of one hand-over are (bl, row, pair) flattened as i = bl*R4 + 4*row + pair
+  int it_bl[MAXI], it_rp[MAXI];
+  const int n_items = SPLIT_SB * R4;
+#pragma unroll
+  for (int m = 0; m < MAXI; m++) {
+    const int i = (tid - NCHAIN) + m * NPROD;
+    it_bl[m] = (!is_chain && i < n_items) ? i / R4 : -1;
+    it_rp[m] = (!is_chain && i < n_items) ? i % R4 : 0;
+  }
+  u64 acc = pack_f2(0.0f, 0.0f);
+  const u64 cvt_mul = pack_f2(1.0f, 0.0625f);
+  const u64 cvt_sub = pack_f2(-12582912.0f, -786432.0f);
+  const int fstride = split_rows * 4;                             // float2 per block in the staging area
+
+  int cur_s = 0;
+  const uint8_t *st = nullptr;
+  int cbk = 0;
+  for (int j = 0; j <= nsub; j++) {
+    if (j < nsub && j % subs_per_chunk == 0) {                    // first hand-over of a ring chunk: wait for its bytes
+      cur_s = ring.s;
+      mbar_wait(&sm.full[cur_s], ring.par);
+      st = sm.stages + (size_t) cur_s * stage_bytes;
+      cbk = min(cb, nb - (j / subs_per_chunk) * cb);
+    }
+    if (!is_chain) {
+      if (j < nsub) {
+        const int bl0 = (j % subs_per_chunk) * SPLIT_SB;          // first block of this hand-over inside the chunk
+        float2 *F = sm.splitF + (size_t) (j & 1) * SPLIT_SB * fstride;
+        float *Sx = sm.splitS + (size_t) (j & 1) * SPLIT_SB * split_rows;
+        const uint32_t *nib = reinterpret_cast<const uint32_t *>(st);
+        const float *sc = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16);
+#pragma unroll
+        for (int m = 0; m < MAXI; m++) {
+          if (it_bl[m] >= 0) {
+            const int bl = bl0 + it_bl[m], r = it_rp[m] >> 2, pr = it_rp[m] & 3;
+            const int b = j * SPLIT_SB + it_bl[m];
+            const uint32_t wv = nib[(bl * R + r) * 4 + pr];
+            const uint4 xv = sm.xq[b * 4 + pr];
+            const int ia = dp4a_us(wv & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
+            const int ib = dp4a_us(wv & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
+            const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
+            float f0, f1;
+            unpack_f2(f, f0, f1);
+            F[it_bl[m] * fstride + it_rp[m]] = make_float2(f0, f1);
+            if (pr == 0) Sx[it_bl[m] * split_rows + r] = __fmul_rn(sc[bl * R + r], sm.dxs[b]);   // _mm256_mul_ps(d0, d1)
+          }
+        }
+      }
+    } else if (j >= 1) {
+      const float2 *F = sm.splitF + (size_t) ((j - 1) & 1) * SPLIT_SB * fstride + cr * 4 + cp;
+      const float *Sx = sm.splitS + (size_t) ((j - 1) & 1) * SPLIT_SB * split_rows + cr;
+      float2 fv[SPLIT_SB];
+      float sv[SPLIT_SB];
+#pragma unroll
+      for (int u = 0; u < SPLIT_SB; u++) { fv[u] = F[u * fstride]; sv[u] = Sx[u * split_rows]; }
+#pragma unroll
+      for (int u = 0; u < SPLIT_SB; u++) acc = ffma2(pack_f2(sv[u], sv[u]), pack_f2(fv[u].x, fv[u].y), acc);   // ggml.c:1457
+    }
+    named_bar_sync(1, MEGA_COMPUTE_THREADS);
+    if (j < nsub && (j % subs_per_chunk == subs_per_chunk - 1 || j == nsub - 1)) {   // chunk fully read by the producers
+      if ((tid & 31) == 0) mbar_arrive(&sm.empty[cur_s]);
+      ring.next(S);
+    }
+  }
+  if (is_chain) {   // horizontal sum exactly as ggml.c:1461-1466 (4 threads of a row hold lanes 2p, 2p+1)
+    float l0, l1;
+    unpack_f2(acc, l0, l1);
+    const float t0 = __fadd_rn(l0, __shfl_xor_sync(0xffffffffu, l0, 2));
+    const float t1 = __fadd_rn(l1, __shfl_xor_sync(0xffffffffu, l1, 2));
+    const float s0 = __fadd_rn(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    if (chain_active && cp == 0) sm.rowres[cr] = __fadd_rn(s0, s1);
+  }
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
+}
+
 __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
-                                              int S, int stage_bytes, int tid) {
+                                              int S, int stage_bytes, int split_rows, int tid) {
   if (rp.R == 0) { named_bar_sync(1, MEGA_COMPUTE_THREADS); return; }
+  if (md.pad != 0) { gemv_rows_split(md, rp, sm, ring, S, stage_bytes, split_rows, tid); return; }   // pad = producer/chain mode
   switch (md.lp) {
     case 1: gemv_rows<1>(md, rp, sm, ring, S, stage_bytes, tid); break;
     case 2: gemv_rows<2>(md, rp, sm, ring, S, stage_bytes, tid); break;
@@ -547,7 +646,9 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   sm.redd = reinterpret_cast<double *>(sm.rowres + MEGA_MAX_ROWS);
   sm.redf = reinterpret_cast<float *>(sm.redd + 32);
   sm.part = sm.redf + 32;
-  sm.full = reinterpret_cast<uint64_t *>(sm.part + MEGA_MAX_NTH * 32);
+  sm.splitF = reinterpret_cast<float2 *>(sm.part + MEGA_MAX_NTH * 32);
+  sm.splitS = reinterpret_cast<float *>(sm.splitF + 2 * SPLIT_SB * a.split_rows * 4);
+  sm.full = reinterpret_cast<uint64_t *>(sm.splitS + 2 * SPLIT_SB * a.split_rows);
   sm.empty = sm.full + S;
   sm.done = reinterpret_cast<volatile uint32_t *>(sm.empty + S);
   return sm;
@@ -700,7 +801,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
     // ---- the mat-vec ----
     const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
-    gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, tid);
+    gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, a.split_rows, tid);
     PROF_MARK();
 
     // ---- epilogue ----
