@@ -85,7 +85,7 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   const int batch = lp == 1 ? 8 : (lp == 2 ? 4 : 2);     // blocks whose loads the row loop issues together
   if (p.cb >= batch) p.cb -= p.cb % batch;
   // small matrices: producer/chain row loop of the whole-token kernel (hands over SPLIT_SB blocks at a time)
-  if (env_int("B200_SPLIT", 1) && p.rmax * 4 <= 128 && p.nb % SPLIT_SB == 0 && p.cb >= SPLIT_SB) {
+  if (env_int("B200_SPLIT", 0) && p.rmax * 4 <= 128 && p.nb % SPLIT_SB == 0 && p.cb >= SPLIT_SB) {
     p.split = 1;
     p.cb -= p.cb % SPLIT_SB;
   }
@@ -651,7 +651,7 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     m->out.split = 0;
     const size_t fixed = (size_t) 2 * SPLIT_SB * m->mega_split_rows * 36 +
                          (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
-                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + MEGA_COMPUTE_WARPS * 4;
+                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;

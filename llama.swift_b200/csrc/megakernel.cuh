@@ -111,6 +111,7 @@ struct MegaSmem {
   double *redd;     // [2][16]
   float *redf;      // [2][16]
   float *part;      // [MEGA_MAX_NTH][32]
+  double2 *ropev;   // [head_dim/2] (cos, sin) of this token's position, fetched once at kernel start
   float2 *splitF;   // [2][SPLIT_SB][split_rows][4]  exact (float)isum pairs, producer warps -> chain warps
   float *splitS;    // [2][SPLIT_SB][split_rows]     d_w*d_x per (block,row)
   uint64_t *full, *empty;
@@ -223,6 +224,16 @@ __device__ __forceinline__ void prologue_plain(const float *x, int nb, const Meg
 __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS][8], const float *norm_w, int nb,
                                                    const MegaSmem &sm, int tid) {
   const int K = nb * 32, items = nb * 4;
+  // the norm weights do not depend on the upstream phase: fetch them now, under the latency of everything below
+  float4 wa[MEGA_NORM_ROUNDS], wc[MEGA_NORM_ROUNDS];
+#pragma unroll
+  for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
+    const int iq = min(tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    wa[rd] = __ldg(reinterpret_cast<const float4 *>(norm_w) + iq * 2);
+    wc[rd] = __ldg(reinterpret_cast<const float4 *>(norm_w) + iq * 2 + 1);
+  }
+  const bool pow2 = (K & (K - 1)) == 0;          // x / 2^k == x * 2^-k exactly: skip the IEEE division routine
+  const double invK = 1.0 / (double) K;
   double s = 0.0;
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
@@ -232,7 +243,7 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
     }
   }
   s = mega_sum_d(s, sm.redd, 0, tid);
-  const double mean = s / (double) K;
+  const double mean = pow2 ? __dmul_rn(s, invK) : s / (double) K;
   double s2 = 0.0;
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
@@ -245,16 +256,15 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
     }
   }
   s2 = mega_sum_d(s2, sm.redd, 1, tid);
-  const float nscale = (float) (1.0 / sqrt(__dadd_rn(s2 / (double) K, (double) 1e-5f)));   // ggml.c:5379
+  const double var = pow2 ? __dmul_rn(s2, invK) : s2 / (double) K;
+  const float nscale = (float) (1.0 / sqrt(__dadd_rn(var, (double) 1e-5f)));               // ggml.c:5379
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
     if (rd * MEGA_COMPUTE_THREADS < items) {      // CTA-uniform: whole rounds only
       const int it = tid + rd * MEGA_COMPUTE_THREADS;
       const bool live = it < items;
       const int iq = live ? it : items - 1;
-      const float4 wa = __ldg(reinterpret_cast<const float4 *>(norm_w) + iq * 2);
-      const float4 wc = __ldg(reinterpret_cast<const float4 *>(norm_w) + iq * 2 + 1);
-      const float w[8] = {wa.x, wa.y, wa.z, wa.w, wc.x, wc.y, wc.z, wc.w};
+      const float w[8] = {wa[rd].x, wa[rd].y, wa[rd].z, wa[rd].w, wc[rd].x, wc[rd].y, wc[rd].z, wc[rd].w};
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) v[i] = __fmul_rn(w[i], __fmul_rn((float) xd[rd][i], nscale));   // y = (float)v; y *= scale; w*y
@@ -573,6 +583,18 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
       if (lane == 0 && j0 + u < p_valid) sc[j0 + u] = s;
     }
   }
+  // V rows of this warp's first chain do not depend on the scores: get the first batch on its way before the soft_max
+  const int nth = a.n_threads;
+  const int dc = (p_part + nth - 1) / nth;
+  const float *vp = L.v_layer + h * HD + qr * 32 + lane;
+  constexpr int VB = 16;
+  float vpre[VB];
+  {
+    const int j0 = warp * dc;
+    const int j1 = warp < nth ? min(min(j0 + dc, p_part), p_valid) : j0;
+#pragma unroll
+    for (int i = 0; i < VB; i++) vpre[i] = (j0 + i < j1) ? __ldcg(vp + (size_t) (j0 + i) * E) : 0.0f;
+  }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
   // soft_max, ggml.c:7019-7041
   float mx = -CUDART_INF_F;
@@ -590,14 +612,17 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   for (int j = tid; j < p_valid; j += MEGA_COMPUTE_THREADS) sc[j] = __fmul_rn(sc[j], inv);   // ggml_vec_scale_f32, ggml.c:7041
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
   // V.P: reference thread t owns columns [t*dc, (t+1)*dc) (ggml.c:5628-5632), FINALIZE adds buffers in order (5570-5574)
-  const int nth = a.n_threads;
-  const int dc = (p_part + nth - 1) / nth;
-  const float *vp = L.v_layer + h * HD + qr * 32 + lane;
   for (int t = warp; t < nth; t += NW) {
     const int j0 = t * dc;
     const int j1 = min(min(j0 + dc, p_part), p_valid);
     float acc = 0.0f;
     int j = j0;
+    if (t == warp) {   // the pre-loaded batch (same order: positions j0, j0+1, ...)
+#pragma unroll
+      for (int i = 0; i < VB; i++)
+        if (j0 + i < j1) acc = fmaf(vpre[i], sc[j0 + i], acc);                  // vec_mad_f32, ggml.c:1696
+      j = min(j0 + VB, j1);
+    }
     for (; j + 16 <= j1; j += 16) {
       float vv[16];
 #pragma unroll
@@ -646,7 +671,8 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   sm.redd = reinterpret_cast<double *>(sm.rowres + MEGA_MAX_ROWS);
   sm.redf = reinterpret_cast<float *>(sm.redd + 32);
   sm.part = sm.redf + 32;
-  sm.splitF = reinterpret_cast<float2 *>(sm.part + MEGA_MAX_NTH * 32);
+  sm.ropev = reinterpret_cast<double2 *>(sm.part + MEGA_MAX_NTH * 32);
+  sm.splitF = reinterpret_cast<float2 *>(sm.ropev + 64);
   sm.splitS = reinterpret_cast<float *>(sm.splitF + 2 * SPLIT_SB * a.split_rows * 4);
   sm.full = reinterpret_cast<uint64_t *>(sm.splitS + 2 * SPLIT_SB * a.split_rows);
   sm.empty = sm.full + S;
@@ -672,12 +698,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   __syncthreads();
 
   if (tid >= MEGA_COMPUTE_THREADS) {
-    if (tid == MEGA_COMPUTE_THREADS) {
-      // ===== TMA loader: the whole token's weight stream for this SM, in schedule order.  With l2_ahead > 0 a second
-      // cursor runs that many chunks further down the same schedule and pulls them from HBM into L2
-      // (cp.async.bulk.prefetch.L2) so that HBM keeps streaming while the ring is full =====
+    // ===== TMA loader warp: the whole token's weight stream for this SM, in schedule order (lane 0).  With
+    // l2_ahead > 0 the whole warp also runs a second cursor that many chunks further down the same schedule and pulls
+    // those lines from HBM into L2 with prefetch.global.L2 (LSU path: the TMA unit is already busy with the demand
+    // stream -- cp.async.bulk.prefetch.L2 through it made things slower), so HBM keeps streaming while the ring is full =====
+    const int lane = tid - MEGA_COMPUTE_THREADS;
+    const bool pf_on = a.l2_ahead > 0;
+    if (lane == 0 || pf_on) {
       RingPos g = {0, 0u, 0u};
       uint32_t done_min = 0;
+      (void) done_min;
       const int n_mats = 4 * a.n_layer + 1;
       int pm_idx = 0, pk = 0;            // prefetch cursor: matrix index in the schedule, chunk within it
       uint32_t pg = 0;                   // global index of the next chunk to prefetch
@@ -688,33 +718,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         const int nchunks = (md.nb + md.cb - 1) / md.cb;
         const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
         for (int k = 0; k < nchunks; k++, g.next(S)) {
-          const int s = g.s;
+          if (lane == 0) {
+            const int s = g.s;
 #if B200_DONE_FLAGS
-          if (g.g >= (uint32_t) S) {
-            const uint32_t need = g.g - (uint32_t) S + 1u;
-            if (done_min < need) {
-              const long long t0 = clock64();
-              for (;;) {
-                uint32_t mn = 0xffffffffu;
+            if (g.g >= (uint32_t) S) {
+              const uint32_t need = g.g - (uint32_t) S + 1u;
+              if (done_min < need) {
+                const long long t0 = clock64();
+                for (;;) {
+                  uint32_t mn = 0xffffffffu;
 #pragma unroll
-                for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) mn = min(mn, sm.done[w]);
-                done_min = mn;
-                if (mn >= need) break;
-                if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+                  for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) mn = min(mn, sm.done[w]);
+                  done_min = mn;
+                  if (mn >= need) break;
+                  if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-          }
 #else
-          // g.par is the parity of the fill about to start; the slot is free once the consumers released the previous
-          // fill (parity par ^ 1).  On a fresh barrier that wait returns at once (the first lap needs no release).
-          mbar_wait(&sm.empty[s], g.par ^ 1u);
+            // g.par is the parity of the fill about to start; the slot is free once the consumers released the
+            // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
+            mbar_wait(&sm.empty[s], g.par ^ 1u);
 #endif
-          const int cbk = min(md.cb, md.nb - k * md.cb);
-          const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
-          mbar_arrive_expect_tx(&sm.full[s], bytes);
-          tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
-          if (a.l2_ahead > 0) {
+            const int cbk = min(md.cb, md.nb - k * md.cb);
+            const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
+            mbar_arrive_expect_tx(&sm.full[s], bytes);
+            tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
+          }
+          if (pf_on) {
+            __syncwarp();
             // keep chunks (g.g + S, g.g + S + l2_ahead] of the stream on their way into L2
             const uint32_t lo = g.g + 1u + (uint32_t) S, hi = lo + (uint32_t) a.l2_ahead;
             while (pm_idx < n_mats && pg < hi) {
@@ -724,7 +757,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
               if (pk >= pn) { pm_idx++; pk = 0; continue; }
               if (pg >= lo) {
                 const int pc = min(pd.cb, pd.nb - pk * pd.cb);
-                l2_prefetch_bulk(pd.w + (size_t) pr.row0 * pd.nb * 20 + (size_t) pk * pd.cb * pr.R * 20, (uint32_t) pc * pr.R * 20);
+                const uint8_t *pp = pd.w + (size_t) pr.row0 * pd.nb * 20 + (size_t) pk * pd.cb * pr.R * 20;
+                const int pbytes = pc * pr.R * 20;
+                for (int off = lane * 128; off < pbytes; off += 32 * 128)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off));
               }
               pk++; pg++;
             }
@@ -741,6 +777,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // mat-vec).  Descriptors come from the kernel parameter block (constant bank).
   const int E = a.n_embd, HD = E / a.n_head;
   const int pos = a.sp->pos;
+  if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
   unsigned int phase = 0;
   int pm = 0;
@@ -813,7 +850,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         const int which = g / E, col = g - which * E;
         float y0 = sm.rowres[2 * i], y1 = sm.rowres[2 * i + 1];
         if (which < 2) {
-          const double2 cs = a.rope[(size_t) pos * (HD / 2) + (col % HD) / 2];
+          const double2 cs = sm.ropev[(col % HD) / 2];
           const double x0 = y0, x1 = y1;
           y0 = (float) __dsub_rn(__dmul_rn(x0, cs.x), __dmul_rn(x1, cs.y));
           y1 = (float) __dadd_rn(__dmul_rn(x0, cs.y), __dmul_rn(x1, cs.x));
