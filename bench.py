@@ -170,8 +170,18 @@ def main():
             return 0
         path = ensure_model(args.layers)
         cores = os.cpu_count() or 1
-        nth = min(cores, 32)
-        tps, n, desc = time_reference_cpu(path, nth, budget_s=150.0, max_steps=max(3, min(steps, 54)))
+        # "all the host threads it can use": the reference's spin-wait pool (ggml.c:9061-9107, re-created on every
+        # llama_eval) gets SLOWER past a point, so calibrate on 3 steps each and time the fastest setting
+        cands = sorted({c for c in (8, 16, 32, 64) if c <= cores} | {min(cores, 8)})
+        cal = {}
+        for c in cands:
+            r, _, _ = time_reference_cpu(path, c, budget_s=20.0, max_steps=3)
+            if r is not None:
+                cal[c] = r
+        nth = max(cal, key=cal.get) if cal else min(cores, 8)
+        tps, n, desc = time_reference_cpu(path, nth, budget_s=120.0, max_steps=max(3, min(steps, 54)))
+        if tps is not None:
+            desc += "; thread-count calibration tok/s: " + ", ".join(f"{c}: {v:.2f}" for c, v in sorted(cal.items())) + f" of {cores} host cores"
         if tps is None:
             print(json.dumps({"impl": "reference", "unavailable": desc}))
             return 0
