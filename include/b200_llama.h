@@ -86,6 +86,11 @@ int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, l
 int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out,
                      int lane_pairs, float *kernel_ms, char *err, size_t errlen);
 
+/* Same for Q4_1 (ggml per-row layout [nb f32 min][nb f32 d][nb*16 B]): ggml_compute_forward_mul_mat_q4_1_f32,
+ * ggml.c:6287-6585 (quantize_row_q4_1 ggml.c:606-648 + ggml_vec_dot_q4_1 ggml.c:1584-1626). */
+int b200_q4_1_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, float *kernel_ms,
+                     char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

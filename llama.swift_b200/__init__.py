@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     L.b200_llama_set_option.argtypes, L.b200_llama_set_option.restype = [vp, cp, ci], ci
     L.b200_q4_0_matvec.argtypes = [ci, vp, ci, ci, vp, vp, ci, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_0_matvec.restype = ci
+    L.b200_q4_1_matvec.argtypes = [ci, vp, ci, ci, vp, vp, C.POINTER(C.c_float), cp, sz]
+    L.b200_q4_1_matvec.restype = ci
     _lib = L
     return L
 
@@ -181,6 +183,21 @@ def q4_0_matvec(w_blocks: np.ndarray, x: np.ndarray, lane_pairs: int = 0, device
     err = C.create_string_buffer(512)
     rc = lib().b200_q4_0_matvec(device, w.ctypes.data, M, K, x.ctypes.data, out.ctypes.data, lane_pairs,
                                 C.byref(ms) if timed else None, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return (out, ms.value) if timed else out
+
+
+def q4_1_matvec(w_rows: np.ndarray, x: np.ndarray, device: int = 0, timed: bool = False):
+    """out[M] = W (Q4_1, ggml per-row layout) * x through the Q4_1 mat-vec kernel."""
+    w = np.ascontiguousarray(w_rows, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    K = x.shape[0]
+    M = w.size // (K // 32 * 24)
+    out = np.empty(M, dtype=np.float32)
+    ms = C.c_float(0)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_q4_1_matvec(device, w.ctypes.data, M, K, x.ctypes.data, out.ctypes.data, C.byref(ms) if timed else None, err, 512)
     if rc != 0:
         raise LlamaError(rc, err.value.decode(errors="replace"))
     return (out, ms.value) if timed else out

@@ -20,6 +20,7 @@
 
 #include "../../include/b200_llama.h"
 #include "kernels.cuh"
+#include "kernels_q4_1.cuh"
 #include "megakernel.cuh"
 
 namespace b200 {
@@ -52,6 +53,7 @@ void set_err(char *err, size_t errlen, const char *fmt, ...) {
   } while (0)
 
 struct GemvPlan {
+  int qtype = 2;            // 2 = Q4_0 (20 B / 32 weights), 3 = Q4_1 (24 B / 32 weights)
   int split = 0;            // whole-token kernel runs this matrix in producer/chain mode
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
@@ -67,8 +69,9 @@ int env_int(const char *name, int dflt) {
 int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 32768) & ~127; }
 
 // Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
-GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
+GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   GemvPlan p;
+  p.qtype = qtype;
   p.M = M;
   p.nb = K / 32;
   const int Mpad = (M + 3) & ~3;
@@ -78,6 +81,21 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override) {
   int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);   // measured best on B200 (profiles/r1_b_*)
   if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
   while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;
+  if (qtype == 3) {
+    // Q4_1: one thread per row (the reference dot is a single sequential chain per row); at least 4 compute warps
+    // for the prologue.  Stage = cb blocks x rmax rows x 24 B; smem also holds the dequantized activation (K floats).
+    p.lp = 4;
+    p.threads = std::max(128, (p.rmax + 31) & ~31) + 32;
+    p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 24)));
+    p.stage_bytes = (p.cb * p.rmax * 24 + 127) & ~127;
+    const int nch = (p.nb + p.cb - 1) / p.cb;
+    const size_t fx = (size_t) K * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+    int S1 = (int) ((kSmemBudget - fx - 256) / (p.stage_bytes + 16));
+    p.S = std::max(1, std::min(S1, nch));
+    p.smem = (size_t) p.S * p.stage_bytes + fx + (size_t) 2 * p.S * 8;
+    p.bytes = (size_t) p.g_total * 4 * p.nb * 24;
+    return p;
+  }
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
   // one ring-stage holds one chunk in both the per-matrix kernels and the whole-token kernel
@@ -126,10 +144,32 @@ cudaError_t launch_gemv_lp(const GemvPlan &p, const GemvArgs &a, cudaStream_t st
 }
 
 template <int PRO, int EPI>
+cudaError_t launch_gemv_q41(const GemvPlan &p, const GemvArgs &a, cudaStream_t st, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.n_cta);
+  cfg.blockDim = dim3(p.threads);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, q4_1_gemv_kernel<PRO, EPI>, a);
+}
+
+// Q4_0 or Q4_1 by the plan's type
+template <int PRO, int EPI>
+cudaError_t launch_gemv(const GemvPlan &p, const GemvArgs &a, cudaStream_t st, bool pdl) {
+  return p.qtype == 3 ? launch_gemv_q41<PRO, EPI>(p, a, st, pdl) : launch_gemv_lp<PRO, EPI>(p, a, st, pdl);
+}
+
+template <int PRO, int EPI>
 cudaError_t configure_gemv() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(q4_gemv_kernel<1, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(q4_gemv_kernel<2, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_1_gemv_kernel<PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(q4_gemv_kernel<4, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
 }
 
@@ -232,7 +272,7 @@ MatDesc mat_desc(const GemvPlan &p) {
 }
 
 bool mega_usable(const b200_llama *m, int n_threads) {
-  return m->opt_mega && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
+  return m->opt_mega && m->f16 == 2 && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
 }
 
 // The whole token as ONE cooperative launch of the persistent kernel (megakernel.cuh).
@@ -270,7 +310,7 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
   cudaError_t e;
   const int E = m->n_embd;
   long long n = 0;
-  e = launch_small(embed_kernel, dim3((E + 255) / 256), dim3(256), 0, st, pdl,
+  e = launch_small(m->f16 == 3 ? embed_q4_1_kernel : embed_kernel, dim3((E + 255) / 256), dim3(256), 0, st, pdl,
                    (const uint8_t *) m->d_tok_emb, (const StepParams *) m->d_sp, m->d_inpL, E);
   if (e != cudaSuccess) return e;
   n++;
@@ -282,7 +322,7 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
       GemvArgs a = base_args(L.qkv);
       a.x = m->d_inpL; a.norm_w = L.attn_norm; a.q_out = m->d_q; a.k_layer = k_layer; a.v_layer = v_layer;
       a.rope = m->d_rope; a.sp = m->d_sp; a.n_embd = E; a.head_dim = E / m->n_head;
-      e = launch_gemv_lp<PRO_NORM, EPI_QKV>(L.qkv, a, st, pdl);
+      e = launch_gemv<PRO_NORM, EPI_QKV>(L.qkv, a, st, pdl);
       if (e != cudaSuccess) return e;
       n++;
     }
@@ -297,21 +337,21 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
     {  // wo, + inpSA                                                              PO.mm:649-654
       GemvArgs a = base_args(L.wo);
       a.x = m->d_att; a.out = m->d_inpFF; a.resid = m->d_inpL;
-      e = launch_gemv_lp<PRO_PLAIN, EPI_RESID>(L.wo, a, st, pdl);
+      e = launch_gemv<PRO_PLAIN, EPI_RESID>(L.wo, a, st, pdl);
       if (e != cudaSuccess) return e;
       n++;
     }
     {  // norm * ffn_norm -> w1|w3 -> silu(w1 x) * (w3 x)                         PO.mm:660-680
       GemvArgs a = base_args(L.w13);
       a.x = m->d_inpFF; a.norm_w = L.ffn_norm; a.out = m->d_h; a.silu_table = m->d_silu;
-      e = launch_gemv_lp<PRO_NORM, EPI_SILU_MUL>(L.w13, a, st, pdl);
+      e = launch_gemv<PRO_NORM, EPI_SILU_MUL>(L.w13, a, st, pdl);
       if (e != cudaSuccess) return e;
       n++;
     }
     {  // w2, + inpFF                                                              PO.mm:682-687
       GemvArgs a = base_args(L.w2);
       a.x = m->d_h; a.out = m->d_inpL; a.resid = m->d_inpFF;
-      e = launch_gemv_lp<PRO_PLAIN, EPI_RESID>(L.w2, a, st, pdl);
+      e = launch_gemv<PRO_PLAIN, EPI_RESID>(L.w2, a, st, pdl);
       if (e != cudaSuccess) return e;
       n++;
     }
@@ -319,7 +359,7 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
   {  // final norm * norm.weight -> output                                       PO.mm:694-706
     GemvArgs a = base_args(m->out);
     a.x = m->d_inpL; a.norm_w = m->d_norm; a.out = m->d_logits;
-    e = launch_gemv_lp<PRO_NORM, EPI_STORE>(m->out, a, st, pdl);
+    e = launch_gemv<PRO_NORM, EPI_STORE>(m->out, a, st, pdl);
     if (e != cudaSuccess) return e;
     n++;
   }
@@ -365,11 +405,15 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<const Ho
   }
   const long long total = (long long) p.g_total * 4 * p.nb;
   const int threads = 256;
-  repack_q4_0_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
-      d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
+  if (p.qtype == 3)
+    repack_q4_1_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
+        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
+  else
+    repack_q4_0_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
+        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  m->weight_bytes += (long long) p.M * p.nb * 20;
+  m->weight_bytes += (long long) p.M * p.nb * (p.qtype == 3 ? 24 : 20);
   return cudaStreamSynchronize(m->stream);
 }
 
@@ -432,6 +476,10 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   auto np = kNParts.find(m->n_embd);
   if (np == kNParts.end()) { set_err(err, errlen, "unsupported n_embd %d (LLAMA_N_PARTS has no entry)", m->n_embd); return fail_code; }   // PO.mm:136 throws
   const int n_parts = np->second;
+  if (m->f16 == 3 && n_parts != 1) {   // the reference merges column-split Q4_1 parts as if rows were AoS (PO.mm:467-477), which they are not
+    set_err(err, errlen, "multi-part Q4_1 model files are not supported (the reference's own merge of them is ill-defined)");
+    return fail_code;
+  }
   if (m->n_embd % m->n_head != 0 || m->n_embd / m->n_head != 128) {
     set_err(err, errlen, "unsupported head size %d (kernels are built for 128)", m->n_embd / std::max(1, m->n_head));
     return fail_code;
@@ -445,9 +493,9 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     fin.read(&m->id_to_token[i][0], len);
   }
   switch (m->f16) {                                                                                         // PO.mm:169-180
-    case 2: break;
-    case 0: case 1: case 3:
-      set_err(err, errlen, "model file '%s' has weight type %d; this build accelerates Q4_0 (type 2) only", path, m->f16);
+    case 2: case 3: break;
+    case 0: case 1:
+      set_err(err, errlen, "model file '%s' has weight type %d; this build accelerates Q4_0 / Q4_1 (types 2, 3) only", path, m->f16);
       return fail_code;
     default:
       set_err(err, errlen, "invalid model file '%s' (bad f16 value %d)", path, m->f16);
@@ -458,10 +506,12 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
 
   // expected tensors, PO.mm:246-286
   const int E = m->n_embd, F = m->n_ff, V = m->n_vocab;
+  const int QT = m->f16;
+  const size_t BPB = QT == 3 ? 24 : 20;    // bytes per 32-weight block (ggml.c:2039-2040)
   std::map<std::string, HostTensor> tensors;
   auto expect = [&](const std::string &name, int ne0, int ne1, int n_dims) {
     HostTensor t; t.n_dims = n_dims; t.ne[0] = ne0; t.ne[1] = ne1;
-    t.data.resize(n_dims == 1 ? (size_t) ne0 * 4 : (size_t) ne1 * (ne0 / 32) * 20);
+    t.data.resize(n_dims == 1 ? (size_t) ne0 * 4 : (size_t) ne1 * (ne0 / 32) * BPB);
     tensors[name] = std::move(t);
   };
   expect("tok_embeddings.weight", E, V, 2);
@@ -524,14 +574,14 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
                   split_type == 0 ? t.ne[0] / n_parts : t.ne[0], split_type == 0 ? t.ne[1] : t.ne[1] / n_parts, ne[0], ne[1]);
           return fail_code;
         }
-        if (ftype != 2) { set_err(err, errlen, "tensor '%s': ftype %d in a Q4_0 model file", name.c_str(), ftype); return fail_code; }
+        if (ftype != QT) { set_err(err, errlen, "tensor '%s': ftype %d in a type-%d model file", name.c_str(), ftype, QT); return fail_code; }
         if (ne[0] % 64 != 0) { set_err(err, errlen, "tensor '%s': row length %d is not a multiple of 64", name.c_str(), ne[0]); return fail_code; }   // PO.mm:437
-        const size_t row_size = (size_t) t.ne[0] / 32 * 20;
+        const size_t row_size = (size_t) t.ne[0] / 32 * BPB;
         if (n_parts == 1) {
           fp.read((char *) t.data.data(), t.data.size());
         } else if (split_type == 0) {                                                                       // PO.mm:467-477
           for (int i1 = 0; i1 < ne[1]; ++i1) {
-            const size_t offset = (size_t) i1 * row_size + ((size_t) part * ne[0] / 32) * 20;
+            const size_t offset = (size_t) i1 * row_size + ((size_t) part * ne[0] / 32) * BPB;
             fp.read((char *) t.data.data() + offset, row_size / n_parts);
           }
         } else {                                                                                            // PO.mm:478-487
@@ -559,7 +609,7 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   CUDA_TRY(cudaEventCreate(&m->ev0));
   CUDA_TRY(cudaEventCreate(&m->ev1));
 
-  const size_t stage_cap = std::max({(size_t) 3 * E * (E / 32) * 20, (size_t) 2 * F * (E / 32) * 20, (size_t) V * (E / 32) * 20});
+  const size_t stage_cap = std::max({(size_t) 3 * E * (E / 32) * BPB, (size_t) 2 * F * (E / 32) * BPB, (size_t) V * (E / 32) * BPB});
   uint8_t *d_stage = nullptr;
   CUDA_TRY(cudaMalloc(&d_stage, stage_cap));
   struct StageGuard { uint8_t *p; ~StageGuard() { cudaFree(p); } } sguard{d_stage};
@@ -574,18 +624,18 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   for (int i = 0; i < m->n_layer; i++) {
     const std::string p = "layers." + std::to_string(i) + ".";
     b200_llama::Layer &L = m->layers[i];
-    L.qkv = make_plan(3 * E, E, m->n_sm, lp_qkv);
+    L.qkv = make_plan(3 * E, E, m->n_sm, lp_qkv, QT);
     CUDA_TRY(upload_matrix(m, L.qkv, {&tensors[p + "attention.wq.weight"], &tensors[p + "attention.wk.weight"], &tensors[p + "attention.wv.weight"]}, 0, d_stage));
-    L.wo = make_plan(E, E, m->n_sm, lp_small);
+    L.wo = make_plan(E, E, m->n_sm, lp_small, QT);
     CUDA_TRY(upload_matrix(m, L.wo, {&tensors[p + "attention.wo.weight"]}, 0, d_stage));
-    L.w13 = make_plan(2 * F, E, m->n_sm, lp_w13);
+    L.w13 = make_plan(2 * F, E, m->n_sm, lp_w13, QT);
     CUDA_TRY(upload_matrix(m, L.w13, {&tensors[p + "feed_forward.w1.weight"], &tensors[p + "feed_forward.w3.weight"]}, F, d_stage));
-    L.w2 = make_plan(E, F, m->n_sm, lp_small);
+    L.w2 = make_plan(E, F, m->n_sm, lp_small, QT);
     CUDA_TRY(upload_matrix(m, L.w2, {&tensors[p + "feed_forward.w2.weight"]}, 0, d_stage));
     CUDA_TRY(upload_f32(tensors[p + "attention_norm.weight"], &L.attn_norm));
     CUDA_TRY(upload_f32(tensors[p + "ffn_norm.weight"], &L.ffn_norm));
   }
-  m->out = make_plan(V, E, m->n_sm, lp_out);
+  m->out = make_plan(V, E, m->n_sm, lp_out, QT);
   CUDA_TRY(upload_matrix(m, m->out, {&tensors["output.weight"]}, 0, d_stage));
   CUDA_TRY(upload_f32(tensors["norm.weight"], &m->d_norm));
   {
@@ -832,8 +882,8 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   return -1;
 }
 
-int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, int lane_pairs,
-                     float *kernel_ms, char *err, size_t errlen) {
+static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int K, const float *x, float *out, int lane_pairs,
+                          float *kernel_ms, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { set_err(err, errlen, "no CUDA device available (this library has no CPU path)"); return fail_code; }
@@ -844,9 +894,9 @@ int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *
   b200_llama tmp;   // only stream / counters are used by upload_matrix
   tmp.device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
-  GemvPlan p = make_plan(M, K, env_int("B200_NUM_CTAS", prop.multiProcessorCount), lane_pairs);
+  GemvPlan p = make_plan(M, K, env_int("B200_NUM_CTAS", prop.multiProcessorCount), lane_pairs, qtype);
   HostTensor t;
-  t.data.assign((const uint8_t *) w_ggml, (const uint8_t *) w_ggml + (size_t) M * (K / 32) * 20);
+  t.data.assign((const uint8_t *) w_ggml, (const uint8_t *) w_ggml + (size_t) M * (K / 32) * (qtype == 3 ? 24 : 20));
   uint8_t *d_stage = nullptr;
   float *d_x = nullptr, *d_out = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -872,7 +922,7 @@ int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *
   float best = 1e30f;
   for (int i = 0; i < reps; i++) {
     MV_TRY(cudaEventRecord(e0, tmp.stream));
-    MV_TRY((launch_gemv_lp<PRO_PLAIN, EPI_STORE>(p, a, tmp.stream, false)));
+    MV_TRY((launch_gemv<PRO_PLAIN, EPI_STORE>(p, a, tmp.stream, false)));
     MV_TRY(cudaEventRecord(e1, tmp.stream));
     MV_TRY(cudaStreamSynchronize(tmp.stream));
     float ms = 0;
@@ -884,6 +934,16 @@ int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *
 #undef MV_TRY
   cleanup();
   return rc;
+}
+
+int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, int lane_pairs,
+                     float *kernel_ms, char *err, size_t errlen) {
+  return q4_matvec_impl(2, device, w_ggml, M, K, x, out, lane_pairs, kernel_ms, err, errlen);
+}
+
+int b200_q4_1_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, float *kernel_ms,
+                     char *err, size_t errlen) {
+  return q4_matvec_impl(3, device, w_ggml, M, K, x, out, 0, kernel_ms, err, errlen);
 }
 
 }  // extern "C"

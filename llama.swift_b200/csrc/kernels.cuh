@@ -99,6 +99,50 @@ __device__ __forceinline__ double block_sum_d(double v, double *red, int tid, in
   return s;
 }
 
+// ---- epilogue shared by the Q4_0 and Q4_1 mat-vec kernels: the graph nodes that consume the row results ------------
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, const RowPart rp, const float *rowres, int tid, int nt) {
+  const int R = rp.R;
+  if (EPI == EPI_STORE || EPI == EPI_RESID) {
+    for (int i = tid; i < R; i += nt) {
+      const int g = rp.row0 + i;
+      if (g < a.M) a.out[g] = (EPI == EPI_RESID) ? __fadd_rn(rowres[i], a.resid[g]) : rowres[i];   // ggml_add, PO.mm:654,687
+    }
+  } else if (EPI == EPI_SILU_MUL) {
+    // fused rows 2i = w1 row i, 2i+1 = w3 row i: silu(w1 x) * (w3 x), PO.mm:678-680; silu via the fp16 table (ggml.c:1955-1963)
+    for (int i = tid; i < R / 2; i += nt) {
+      const int g = rp.row0 / 2 + i;
+      if (2 * g < a.M) {
+        const uint16_t hx = __half_as_ushort(__float2half_rn(rowres[2 * i]));
+        const float sv = __half2float(__ushort_as_half(a.silu_table[hx]));
+        a.out[g] = __fmul_rn(sv, rowres[2 * i + 1]);
+      }
+    }
+  } else {
+    // fused rows [0,E) = wq, [E,2E) = wk, [2E,3E) = wv.  RoPE (ggml.c:7110-7127) on Q and K pairs in double, K/V
+    // stored to the cache row of this position (PO.mm:585-611: cpy then in-place rope == rope then store).
+    const int E = a.n_embd;
+    const int pos = a.sp->pos;
+    for (int i = tid; i < R / 2; i += nt) {
+      const int g = rp.row0 + 2 * i;
+      if (g >= a.M) continue;
+      const int which = g / E, col = g - which * E;
+      float y0 = rowres[2 * i], y1 = rowres[2 * i + 1];
+      if (which < 2) {
+        const double2 cs = a.rope[(size_t) pos * (a.head_dim / 2) + (col % a.head_dim) / 2];
+        const double x0 = y0, x1 = y1;
+        y0 = (float) __dsub_rn(__dmul_rn(x0, cs.x), __dmul_rn(x1, cs.y));
+        y1 = (float) __dadd_rn(__dmul_rn(x0, cs.y), __dmul_rn(x1, cs.x));
+      }
+      float *dst = which == 0 ? a.q_out + col
+                 : which == 1 ? a.k_layer + (size_t) pos * E + col
+                              : a.v_layer + (size_t) pos * E + col;
+      dst[0] = y0;
+      dst[1] = y1;
+    }
+  }
+}
+
 template <int LP, int PRO, int EPI>
 __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -283,45 +327,7 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   if (active && pg == 0) rowres[r] = res;
   named_bar_sync(1, nt);
 
-  // ---- epilogue: the graph nodes that consume this mat-vec ----
-  if (EPI == EPI_STORE || EPI == EPI_RESID) {
-    for (int i = tid; i < R; i += nt) {
-      const int g = rp.row0 + i;
-      if (g < a.M) a.out[g] = (EPI == EPI_RESID) ? __fadd_rn(rowres[i], a.resid[g]) : rowres[i];   // ggml_add, PO.mm:654,687
-    }
-  } else if (EPI == EPI_SILU_MUL) {
-    // fused rows 2i = w1 row i, 2i+1 = w3 row i: silu(w1 x) * (w3 x), PO.mm:678-680; silu via the fp16 table (ggml.c:1955-1963)
-    for (int i = tid; i < R / 2; i += nt) {
-      const int g = rp.row0 / 2 + i;
-      if (2 * g < a.M) {
-        const uint16_t hx = __half_as_ushort(__float2half_rn(rowres[2 * i]));
-        const float sv = __half2float(__ushort_as_half(a.silu_table[hx]));
-        a.out[g] = __fmul_rn(sv, rowres[2 * i + 1]);
-      }
-    }
-  } else {
-    // fused rows [0,E) = wq, [E,2E) = wk, [2E,3E) = wv.  RoPE (ggml.c:7110-7127) on Q and K pairs in double, K/V
-    // stored to the cache row of this position (PO.mm:585-611: cpy then in-place rope == rope then store).
-    const int E = a.n_embd;
-    const int pos = a.sp->pos;
-    for (int i = tid; i < R / 2; i += nt) {
-      const int g = rp.row0 + 2 * i;
-      if (g >= a.M) continue;
-      const int which = g / E, col = g - which * E;
-      float y0 = rowres[2 * i], y1 = rowres[2 * i + 1];
-      if (which < 2) {
-        const double2 cs = a.rope[(size_t) pos * (a.head_dim / 2) + (col % a.head_dim) / 2];
-        const double x0 = y0, x1 = y1;
-        y0 = (float) __dsub_rn(__dmul_rn(x0, cs.x), __dmul_rn(x1, cs.y));
-        y1 = (float) __dadd_rn(__dmul_rn(x0, cs.y), __dmul_rn(x1, cs.x));
-      }
-      float *dst = which == 0 ? a.q_out + col
-                 : which == 1 ? a.k_layer + (size_t) pos * E + col
-                              : a.v_layer + (size_t) pos * E + col;
-      dst[0] = y0;
-      dst[1] = y1;
-    }
-  }
+  gemv_epilogue<EPI>(a, rp, rowres, tid, nt);
 }
 
 // ---- attention for one token: cluster of 4 CTAs per head ------------------------------------------------------------

@@ -184,3 +184,40 @@ def test_llama_eval_vs_golden_reference_vectors(nth):
         assert np.array_equal(bits(gpu.kv_export(0, 1, n_past)[:, :256]), bits(G[f"eval_v0_nth{nth}"]))
     finally:
         gpu.free()
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (1000, 4096), (4096, 11008), (8, 64)])
+def test_matvec_q4_1_bit_exact(oracle_lib, shape):
+    """mul_mat_q4_1_f32: quantize_row_q4_1 + the scalar, strictly sequential vec_dot_q4_1 chain (ggml.c:1584-1626)."""
+    from llama_swift_b200 import ggml_format as gf
+    M, K = shape
+    w = (RNG.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    wq = gf.quantize_q4_1(w)
+    x = (RNG.standard_normal(K) * 1.7).astype(np.float32)
+    x[:32] = 0.25                                   # constant block: d = 0, id = 0
+    want = np.zeros(M, np.float32)
+    oracle_lib.ora_mul_mat_q4(3, wq.ctypes.data, M, K, x.ctypes.data, 1, want.ctypes.data)
+    got = lsb.q4_1_matvec(wq, x)
+    assert np.array_equal(bits(got), bits(want)), f"max abs diff {np.abs(got - want).max()}"
+
+
+def test_llama_eval_q4_1_vs_oracle(oracle_lib):
+    """A Q4_1 model file (type 3, quantized by the restated utils.cpp quantizer) through llama_eval: bit-identical."""
+    path = model_file(n_layer=1, n_vocab=256, seed=21, ftype=3)
+    ora = CpuModel(oracle_lib, "ora", path, 32)
+    gpu = lsb.llama_model_load(path, n_ctx=32)
+    try:
+        assert gpu.ftype == 3
+        rng = np.random.default_rng(5)
+        n_past = 0
+        for n in (4, 1, 1, 1):
+            toks = rng.integers(3, 256, size=n).astype(np.int32)
+            want = ora.eval(8, n_past, toks)
+            got = lsb.llama_eval(gpu, 8, n_past, toks)
+            same, r = _report(f"q4_1 n_past={n_past} N={n}", got, want)
+            assert r <= 1e-3 and got.argmax() == want.argmax()
+            assert same
+            n_past += n
+    finally:
+        ora.free()
+        gpu.free()

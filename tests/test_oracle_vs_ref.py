@@ -121,3 +121,21 @@ def test_llama_eval_bit_exact(oracle_lib, ref_lib, small_model, n_threads):
     finally:
         ref.free()
         ora.free()
+
+
+def test_llama_eval_q4_1_bit_exact(oracle_lib, ref_lib):
+    """Type-3 (Q4_1) model files: loader + llama_eval of the restatement against the compiled reference."""
+    from conftest import model_file
+    path = model_file(n_layer=1, n_vocab=256, seed=21, ftype=3)
+    ref = CpuModel(ref_lib, "ref_llama", path, 32)
+    ora = CpuModel(oracle_lib, "ora", path, 32)
+    try:
+        rng = np.random.default_rng(5)
+        n_past = 0
+        for n in (4, 1, 1, 1):
+            toks = rng.integers(3, 256, size=n).astype(np.int32)
+            assert np.array_equal(bits(ora.eval(8, n_past, toks)), bits(ref.eval(8, n_past, toks)))
+            n_past += n
+    finally:
+        ref.free()
+        ora.free()
