@@ -150,6 +150,9 @@ def main():
     ap.add_argument("--layers", type=int, default=32, help="debug: fewer layers (the result is then NOT the benchmark)")
     ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
+                    help="N > 1: tp = ONE bs=1 generation over all GPUs (rows of every matrix split over the ranks; the metric "
+                         "BASELINE.json names); replicas = N independent generations")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,7 +212,26 @@ def main():
     path = model_path(args.layers)
 
     n_ctx = N_PROMPT + steps + 8
-    model = lsb.llama_model_load(path, n_ctx=n_ctx, device=local_rank)
+    from llama_swift_b200 import dist_util
+    tp = world > 1 and args.parallelism == "tp"
+    tp_note = None
+    model = None
+    if tp:
+        # one model over all ranks: this rank's row shard + peer-mapped exchange areas (IPC handles over the process group)
+        ok = 1
+        try:
+            model = dist_util.tp_load(lsb, path, n_ctx, local_rank)
+        except Exception as e:  # noqa: BLE001 -- every rank must learn about a failure anywhere
+            ok, tp_note = 0, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if model is not None:
+                model.free()
+            model, tp = None, False
+            tp_note = "tensor-parallel setup failed on some rank (%s); ran independent replicas instead" % (tp_note or "other rank")
+    if model is None:
+        model = lsb.llama_model_load(path, n_ctx=n_ctx, device=local_rank)
     n_vocab = model.n_vocab
 
     def prompt():
@@ -219,8 +241,6 @@ def main():
     first = int(prompt().argmax())
     model.decode_device(N_PROMPT, first, warmup, n_threads=args.threads)
     first = int(prompt().argmax())
-
-    from llama_swift_b200 import dist_util
 
     def sync_all():
         dist_util.barrier_and_sync(torch.cuda.synchronize)
@@ -261,8 +281,11 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    tps = world * steps / (ms_value * 1e-3)
+    jobs = 1 if tp else world            # tp: ONE generation over all GPUs; replicas: one per GPU
+    tps = jobs * steps / (ms_value * 1e-3)
     mean_bytes = float(np.mean([algorithmic_bytes(N_PROMPT + i) for i in range(steps)])) if args.layers == 32 else None
+    if mean_bytes is not None and tp:
+        mean_bytes /= world              # bytes one GPU streams per launch: its row shard of the weights, its heads' KV
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -289,13 +312,22 @@ def main():
         else:
             cpu = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": desc}
 
-    config.update({"parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (tensor-parallel sharding is not built yet)",
-                   "n_ctx": n_ctx, "graph": "CUDA graph replay of [memset, decode_token_kernel] + argmax kernel per step"})
+    if world == 1:
+        par = "1 GPU"
+    elif tp:
+        par = (f"tp{world}: one bs=1 generation over {world} GPUs, every matrix split by rows (wq/wk/wv by head), activation slices "
+               "all-gathered by peer-to-peer stores over NVLink inside the token kernel (no NCCL on the data path); "
+               "roofline is per GPU (bytes of its shard)")
+    else:
+        par = f"{world} independent replicas" + (f" [{tp_note}]" if tp_note else "")
+    config.update({"parallelism": par, "n_ctx": n_ctx,
+                   "graph": "CUDA graph replay of [memset, decode_token_kernel] + argmax kernel per step"})
     line = {"metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_value / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warmup, "ms_per_step": ms_value / steps, "higher_is_better": True,
+            "scaling": "strong" if tp else "weak", "vs_baseline": None,
             "dtype": "int4 x int4 -> int32 block dots (dp4a), fp32 lane accumulation (bit-exact AVX2 order), f32 KV",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": world * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
+            "e2e": {"value": jobs * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
                     "note": "b200_llama_eval per token: token id by value, logits to pinned host memory, host arg-max"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))

@@ -31,6 +31,27 @@ typedef struct b200_llama b200_llama;
  * device: CUDA device ordinal to place the model on. */
 int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen);
 
+/* ---- tensor-parallel groups: one model over the 2 / 4 / 8 GPUs of an NVSwitch box ---------------------------------------
+ * The reference has no multi-GPU path; what it does have is the Megatron-style split of its multi-part model files
+ * (LLAMA_N_PARTS, PO.mm:33-38; merged back at PO.mm:358-388).  Here every weight matrix is split by ROWS over the
+ * group (wq/wk/wv by attention head), so each GPU computes complete reference dot products -- bit-identical to the
+ * single-GPU result -- and the finished activation slices are all-gathered by peer-to-peer stores over NVLink from
+ * inside the token kernel.  Two ways to form a group:
+ *
+ *  (a) one process driving all GPUs -- what a LlamaRunner app needs: b200_llama_load_group returns ONE handle that
+ *      b200_llama_eval / b200_llama_decode_device / b200_llama_free accept like a single-GPU handle;
+ *  (b) one process per GPU (torchrun-style launchers): every rank calls b200_llama_load_shard, publishes its
+ *      b200_llama_tp_ipc_handle (64 bytes) to the other ranks by any means, and calls b200_llama_tp_connect_ipc
+ *      with all ranks' handles (handle i at handles + i * handle_stride).  After that every rank calls
+ *      b200_llama_eval / _decode_device with identical arguments, in lock-step; each gets the full logits. */
+int b200_llama_load_group(const char *path, int n_ctx, const int *devices, int n_devices, b200_llama **out,
+                          char *err, size_t errlen);
+int b200_llama_load_shard(const char *path, int n_ctx, int device, int tp_rank, int tp_size, b200_llama **out,
+                          char *err, size_t errlen);
+#define B200_LLAMA_IPC_HANDLE_BYTES 64
+int b200_llama_tp_ipc_handle(const b200_llama *m, void *handle_out, size_t handle_bytes);
+int b200_llama_tp_connect_ipc(b200_llama *m, const void *handles, size_t handle_stride, char *err, size_t errlen);
+
 /* == llama_eval(model, n_threads, n_past, embd_inp, embd_w, mem_per_token, &err), PO.mm:510-735.
  * Evaluates n_tokens tokens at positions [n_past, n_past + n_tokens), appending their K/V rows, and writes the
  * LAST token's logits (n_vocab floats, PO.mm:724-725) to host memory `logits_out`.  May be called again with a

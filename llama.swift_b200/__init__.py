@@ -50,6 +50,15 @@ def lib() -> C.CDLL:
     vp, ci, cp, sz = C.c_void_p, C.c_int, C.c_char_p, C.c_size_t
     L.b200_llama_load.argtypes = [cp, ci, ci, C.POINTER(vp), cp, sz]
     L.b200_llama_load.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_load_group"):   # (older development A/B builds lack the group API)
+        L.b200_llama_load_group.argtypes = [cp, ci, C.POINTER(ci), ci, C.POINTER(vp), cp, sz]
+        L.b200_llama_load_group.restype = ci
+        L.b200_llama_load_shard.argtypes = [cp, ci, ci, ci, ci, C.POINTER(vp), cp, sz]
+        L.b200_llama_load_shard.restype = ci
+        L.b200_llama_tp_ipc_handle.argtypes = [vp, vp, sz]
+        L.b200_llama_tp_ipc_handle.restype = ci
+        L.b200_llama_tp_connect_ipc.argtypes = [vp, vp, sz, cp, sz]
+        L.b200_llama_tp_connect_ipc.restype = ci
     L.b200_llama_eval.argtypes = [vp, ci, ci, vp, ci, vp, cp, sz]
     L.b200_llama_eval.restype = ci
     L.b200_llama_free.argtypes = [vp]
@@ -158,6 +167,49 @@ def llama_model_load(fname: str, n_ctx: int = 512, device: int = 0) -> LlamaMode
     if rc != 0:
         raise LlamaError(rc, err.value.decode(errors="replace"))
     return LlamaModel(h.value)
+
+
+def llama_model_load_group(fname: str, n_ctx: int = 512, devices=(0, 1)) -> LlamaModel:
+    """One model over several GPUs driven by this process (tensor parallel, rows of every matrix split over the
+    group; include/b200_llama.h).  The returned handle is used exactly like a single-GPU one."""
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    devs = (C.c_int * len(devices))(*devices)
+    rc = lib().b200_llama_load_group(os.fsencode(fname), n_ctx, devs, len(devices), C.byref(h), err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return LlamaModel(h.value)
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def llama_model_load_shard(fname: str, n_ctx: int, device: int, tp_rank: int, tp_size: int) -> LlamaModel:
+    """Rank tp_rank of a one-process-per-GPU tensor-parallel group; connect it with tp_connect() before evaluating."""
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_load_shard(os.fsencode(fname), n_ctx, device, tp_rank, tp_size, C.byref(h), err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return LlamaModel(h.value)
+
+
+def tp_ipc_handle(model: LlamaModel) -> bytes:
+    buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+    if lib().b200_llama_tp_ipc_handle(model._h, buf, IPC_HANDLE_BYTES) != 0:
+        raise LlamaError(ERR_LOAD, "cudaIpcGetMemHandle failed")
+    return buf.raw
+
+
+def tp_connect(model: LlamaModel, handles) -> None:
+    """handles: every rank's tp_ipc_handle(), in rank order (exchange them with torch.distributed.all_gather_object
+    or any other channel -- that exchange is plumbing and happens once, at load time)."""
+    blob = b"".join(bytes(h) for h in handles)
+    buf = C.create_string_buffer(blob, len(blob))
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_tp_connect_ipc(model._h, buf, IPC_HANDLE_BYTES, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
 
 
 def llama_eval(model: LlamaModel, n_threads: int, n_past: int, embd_inp) -> np.ndarray:

@@ -251,6 +251,18 @@ struct b200_llama {
   int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0, mega_split_rows = 0;
   size_t mega_smem = 0;
 
+  // tensor-parallel group: this handle is rank tp_rank of tp_size; every matrix is split by rows
+  int tp_rank = 0, tp_size = 1;
+  int e_loc = 0, f_loc = 0, v_loc = 0;      // this rank's share of n_embd / n_ff / n_vocab
+  // the exchange area (ONE allocation, so one IPC handle): flagged activations | logits | end-of-token flags
+  uint8_t *d_xchg = nullptr;
+  size_t xchg_ll_bytes = 0, xchg_bytes = 0;
+  uint8_t *peer_xchg[MEGA_MAX_TP] = {};     // every rank's exchange area as mapped into this process / device
+  bool peer_ipc[MEGA_MAX_TP] = {};          // opened with cudaIpcOpenMemHandle (to be closed)
+  bool tp_connected = false;
+  unsigned int *d_epoch = nullptr;
+  std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
+
   int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0, opt_time_kernel = 0;
   double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
   std::vector<cudaEvent_t> kev;
@@ -272,17 +284,28 @@ MatDesc mat_desc(const GemvPlan &p) {
 }
 
 bool mega_usable(const b200_llama *m, int n_threads) {
-  return m->opt_mega && m->f16 == 2 && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
+  return (m->opt_mega || m->tp_size > 1) && m->f16 == 2 && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
 }
 
 // The whole token as ONE cooperative launch of the persistent kernel (megakernel.cuh).
 cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches) {
-  cudaError_t e = cudaMemsetAsync(m->d_bar, 0, sizeof(unsigned int), m->stream);
+  cudaError_t e = cudaMemsetAsync(m->d_bar, 0, 2 * sizeof(unsigned int), m->stream);
   if (e != cudaSuccess) return e;
   TokenArgs &a = *m->h_token_args;     // descriptors were filled in at load time
   a.n_layer = m->n_layer; a.out = mat_desc(m->out); a.final_norm = m->d_norm;
-  a.tok_emb = m->d_tok_emb; a.inpL = m->d_inpL; a.inpFF = m->d_inpFF; a.q = m->d_q; a.att = m->d_att; a.h = m->d_h;
-  a.logits = m->d_logits; a.rope = m->d_rope; a.silu_table = m->d_silu; a.exp_table = m->d_exp; a.sp = m->d_sp;
+  a.tok_emb = m->d_tok_emb; a.q = m->d_q;
+  a.rope = m->d_rope; a.silu_table = m->d_silu; a.exp_table = m->d_exp; a.sp = m->d_sp;
+  a.tp.rank = m->tp_rank; a.tp.size = m->tp_size; a.tp.e_loc = m->e_loc; a.tp.f_loc = m->f_loc; a.tp.v_loc = m->v_loc;
+  for (int p = 0; p < m->tp_size; p++) {
+    uint8_t *base = m->peer_xchg[p];
+    a.tp.ll[p] = reinterpret_cast<uint2 *>(base);
+    a.tp.logits[p] = reinterpret_cast<float *>(base + m->xchg_ll_bytes);
+    a.tp.done[p] = reinterpret_cast<unsigned int *>(base + m->xchg_ll_bytes + (size_t) m->n_vocab * 4);
+  }
+  a.epoch = m->d_epoch;
+  // a spin-wait that outlives this many clock ticks traps instead of hanging the GPU; a multi-GPU group has to
+  // tolerate the launch skew of its processes (graph instantiation, a slow host)
+  a.spin_limit = m->tp_size > 1 ? 40000000000LL : 4000000000LL;
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
@@ -393,15 +416,22 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
 }
 
 // Upload the concatenated raw rows of the fused matrices and repack them into the tile-major stream.
-cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<const HostTensor *> &parts, int interleave_half,
+struct RowSlice { const uint8_t *p; size_t bytes; };   // whole rows of a host tensor (ggml rows are contiguous)
+
+RowSlice rows_of(const HostTensor &t, int row0, int n_rows) {
+  const size_t row_bytes = t.data.size() / (size_t) t.ne[1];
+  return RowSlice{t.data.data() + (size_t) row0 * row_bytes, (size_t) n_rows * row_bytes};
+}
+
+cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice> &parts, int interleave_half,
                           uint8_t *d_stage) {
   cudaError_t e = cudaMalloc(&p.d_w, p.bytes);
   if (e != cudaSuccess) return e;
   size_t off = 0;
-  for (const HostTensor *t : parts) {
-    e = cudaMemcpyAsync(d_stage + off, t->data.data(), t->data.size(), cudaMemcpyHostToDevice, m->stream);
+  for (const RowSlice &t : parts) {
+    e = cudaMemcpyAsync(d_stage + off, t.p, t.bytes, cudaMemcpyHostToDevice, m->stream);
     if (e != cudaSuccess) return e;
-    off += t->data.size();
+    off += t.bytes;
   }
   const long long total = (long long) p.g_total * 4 * p.nb;
   const int threads = 256;
@@ -419,7 +449,12 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<const Ho
 
 void free_model(b200_llama *m) {
   if (!m) return;
+  for (size_t i = 1; i < m->group.size(); i++) free_model(m->group[i]);   // a group leader owns the other ranks
+  m->group.clear();
   cudaSetDevice(m->device);
+  for (int p = 0; p < MEGA_MAX_TP; p++)
+    if (m->peer_ipc[p] && m->peer_xchg[p]) cudaIpcCloseMemHandle(m->peer_xchg[p]);
+  cudaFree(m->d_xchg); cudaFree(m->d_epoch);
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   for (auto &L : m->layers) {
     cudaFree(L.qkv.d_w); cudaFree(L.wo.d_w); cudaFree(L.w13.d_w); cudaFree(L.w2.d_w);
@@ -427,7 +462,7 @@ void free_model(b200_llama *m) {
   }
   cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
-  cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h); cudaFree(m->d_logits);
+  cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h);   // d_logits lives inside d_xchg
   delete m->h_token_args; cudaFree(m->d_bar);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
@@ -440,12 +475,13 @@ void free_model(b200_llama *m) {
 
 const std::map<int, int> kNParts = {{4096, 1}, {5120, 2}, {6656, 4}, {8192, 8}};   // LLAMA_N_PARTS, PO.mm:33-38
 
-}  // namespace
-
-extern "C" {
-
-int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen) {
+// llama_model_load for rank tp_rank of a tensor-parallel group of tp_size GPUs (1 = the whole model on one GPU).
+int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size, b200_llama **out, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_LOAD;
+  if (tp_size < 1 || tp_size > MEGA_MAX_TP || tp_rank < 0 || tp_rank >= tp_size) {
+    set_err(err, errlen, "bad tensor-parallel rank %d of %d (at most %d GPUs)", tp_rank, tp_size, MEGA_MAX_TP);
+    return fail_code;
+  }
   if (!out) { set_err(err, errlen, "null out pointer"); return fail_code; }
   *out = nullptr;
   int n_dev = 0;
@@ -464,6 +500,7 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   b200_llama *m = new b200_llama();
   struct Guard { b200_llama *p; ~Guard() { if (p) free_model(p); } } guard{m};
   m->device = device;
+  m->tp_rank = tp_rank; m->tp_size = tp_size;
   int32_t hp[7] = {0};
   fin.read((char *) hp, sizeof(hp));                                                                        // PO.mm:124-131
   m->n_vocab = hp[0]; m->n_embd = hp[1]; m->n_mult = hp[2]; m->n_head = hp[3]; m->n_layer = hp[4]; m->n_rot = hp[5]; m->f16 = hp[6];
@@ -484,6 +521,14 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     set_err(err, errlen, "unsupported head size %d (kernels are built for 128)", m->n_embd / std::max(1, m->n_head));
     return fail_code;
   }
+  if (tp_size > 1) {
+    if (m->f16 != 2) { set_err(err, errlen, "tensor-parallel groups support Q4_0 model files only (type 2), got type %d", m->f16); return fail_code; }
+    if (m->n_head % tp_size != 0 || m->n_ff % (2 * tp_size) != 0 || m->n_vocab % tp_size != 0) {
+      set_err(err, errlen, "n_head %d / n_ff %d / n_vocab %d do not split over %d GPUs", m->n_head, m->n_ff, m->n_vocab, tp_size);
+      return fail_code;
+    }
+  }
+  m->e_loc = m->n_embd / tp_size; m->f_loc = m->n_ff / tp_size; m->v_loc = m->n_vocab / tp_size;
   m->id_to_token.resize(m->n_vocab);
   for (int i = 0; i < m->n_vocab; i++) {                                                                    // PO.mm:149-163
     uint32_t len = 0;
@@ -621,22 +666,27 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   };
   const int lp_small = env_int("B200_LP_SMALL", 0), lp_qkv = env_int("B200_LP_QKV", 0), lp_w13 = env_int("B200_LP_W13", 0), lp_out = env_int("B200_LP_OUT", 0);
   m->layers.resize(m->n_layer);
+  // Row split over the tensor-parallel group: rank r keeps rows [r*n/tp, (r+1)*n/tp) of every matrix (for wq/wk/wv
+  // these are its heads).  A row is a complete reference dot product, so the split changes no arithmetic.
+  const int El = m->e_loc, Fl = m->f_loc, Vl = m->v_loc;
+  const int e0 = tp_rank * El, f0 = tp_rank * Fl, v0 = tp_rank * Vl;
   for (int i = 0; i < m->n_layer; i++) {
     const std::string p = "layers." + std::to_string(i) + ".";
     b200_llama::Layer &L = m->layers[i];
-    L.qkv = make_plan(3 * E, E, m->n_sm, lp_qkv, QT);
-    CUDA_TRY(upload_matrix(m, L.qkv, {&tensors[p + "attention.wq.weight"], &tensors[p + "attention.wk.weight"], &tensors[p + "attention.wv.weight"]}, 0, d_stage));
-    L.wo = make_plan(E, E, m->n_sm, lp_small, QT);
-    CUDA_TRY(upload_matrix(m, L.wo, {&tensors[p + "attention.wo.weight"]}, 0, d_stage));
-    L.w13 = make_plan(2 * F, E, m->n_sm, lp_w13, QT);
-    CUDA_TRY(upload_matrix(m, L.w13, {&tensors[p + "feed_forward.w1.weight"], &tensors[p + "feed_forward.w3.weight"]}, F, d_stage));
-    L.w2 = make_plan(E, F, m->n_sm, lp_small, QT);
-    CUDA_TRY(upload_matrix(m, L.w2, {&tensors[p + "feed_forward.w2.weight"]}, 0, d_stage));
+    L.qkv = make_plan(3 * El, E, m->n_sm, lp_qkv, QT);
+    CUDA_TRY(upload_matrix(m, L.qkv, {rows_of(tensors[p + "attention.wq.weight"], e0, El), rows_of(tensors[p + "attention.wk.weight"], e0, El),
+                                      rows_of(tensors[p + "attention.wv.weight"], e0, El)}, 0, d_stage));
+    L.wo = make_plan(El, E, m->n_sm, lp_small, QT);
+    CUDA_TRY(upload_matrix(m, L.wo, {rows_of(tensors[p + "attention.wo.weight"], e0, El)}, 0, d_stage));
+    L.w13 = make_plan(2 * Fl, E, m->n_sm, lp_w13, QT);
+    CUDA_TRY(upload_matrix(m, L.w13, {rows_of(tensors[p + "feed_forward.w1.weight"], f0, Fl), rows_of(tensors[p + "feed_forward.w3.weight"], f0, Fl)}, Fl, d_stage));
+    L.w2 = make_plan(El, F, m->n_sm, lp_small, QT);
+    CUDA_TRY(upload_matrix(m, L.w2, {rows_of(tensors[p + "feed_forward.w2.weight"], e0, El)}, 0, d_stage));
     CUDA_TRY(upload_f32(tensors[p + "attention_norm.weight"], &L.attn_norm));
     CUDA_TRY(upload_f32(tensors[p + "ffn_norm.weight"], &L.ffn_norm));
   }
-  m->out = make_plan(V, E, m->n_sm, lp_out, QT);
-  CUDA_TRY(upload_matrix(m, m->out, {&tensors["output.weight"]}, 0, d_stage));
+  m->out = make_plan(Vl, E, m->n_sm, lp_out, QT);
+  CUDA_TRY(upload_matrix(m, m->out, {rows_of(tensors["output.weight"], v0, Vl)}, 0, d_stage));
   CUDA_TRY(upload_f32(tensors["norm.weight"], &m->d_norm));
   {
     const HostTensor &t = tensors["tok_embeddings.weight"];
@@ -670,7 +720,20 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   CUDA_TRY(cudaMalloc(&m->d_q, E * 4));
   CUDA_TRY(cudaMalloc(&m->d_att, E * 4));
   CUDA_TRY(cudaMalloc(&m->d_h, (size_t) F * 4));
-  CUDA_TRY(cudaMalloc(&m->d_logits, (size_t) V * 4));
+  // exchange area: flagged activations inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F] (8 B per value), then the logits,
+  // then the end-of-token flags.  One allocation = one IPC handle; zero-filled, so no flag matches a live sequence number.
+  m->xchg_ll_bytes = ((size_t) 6 * E + (size_t) 2 * F) * 8;
+  m->xchg_bytes = m->xchg_ll_bytes + (size_t) V * 4 + MEGA_MAX_TP * 4 + 256;
+  CUDA_TRY(cudaMalloc(&m->d_xchg, m->xchg_bytes));
+  CUDA_TRY(cudaMemset(m->d_xchg, 0, m->xchg_bytes));
+  m->d_logits = reinterpret_cast<float *>(m->d_xchg + m->xchg_ll_bytes);
+  m->peer_xchg[tp_rank] = m->d_xchg;
+  m->tp_connected = tp_size == 1;
+  CUDA_TRY(cudaMalloc(&m->d_epoch, sizeof(unsigned int)));
+  {
+    const unsigned int one = 1;
+    CUDA_TRY(cudaMemcpy(m->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMalloc(&m->d_sp, sizeof(StepParams)));
   CUDA_TRY(cudaMemset(m->d_sp, 0, sizeof(StepParams)));
   CUDA_TRY(cudaMallocHost(&m->h_logits, (size_t) V * 4));
@@ -687,8 +750,8 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
     m->h_token_args = new TokenArgs();
     memset(m->h_token_args, 0, sizeof(TokenArgs));
     if (m->n_layer <= MEGA_MAX_LAYERS) memcpy(m->h_token_args->layers, descs.data(), descs.size() * sizeof(LayerDesc));
-    CUDA_TRY(cudaMalloc(&m->d_bar, sizeof(unsigned int)));
-    CUDA_TRY(cudaMemset(m->d_bar, 0, sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned int)));
     // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
     const int nb_max = std::max(E, F) / 32;
     m->mega_xs_floats = (n_ctx + 3) & ~3;
@@ -718,8 +781,114 @@ int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, c
   m->opt_graph = env_int("B200_GRAPH", 1);
   m->opt_pdl = env_int("B200_PDL", 0);
 
+  if (tp_size > 1 && !(m->f16 == 2 && m->mega_S >= 2)) {
+    set_err(err, errlen, "this model's shapes do not fit the whole-token kernel, which a tensor-parallel group requires");
+    return fail_code;
+  }
   *out = m;
   guard.p = nullptr;
+  return B200_LLAMA_OK;
+}
+
+// checks shared by the entry points that launch the token kernel
+const char *tp_ready(const b200_llama *m, int n_threads) {
+  if (m->tp_size > 1 && !m->tp_connected) return "tensor-parallel group is not connected (b200_llama_tp_connect_ipc / b200_llama_load_group)";
+  if (m->tp_size > 1 && n_threads > MEGA_MAX_NTH) return "a tensor-parallel group supports n_threads <= 16";
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_llama_load(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen) {
+  return load_impl(path, n_ctx, device, 0, 1, out, err, errlen);
+}
+
+int b200_llama_load_shard(const char *path, int n_ctx, int device, int tp_rank, int tp_size, b200_llama **out,
+                          char *err, size_t errlen) {
+  return load_impl(path, n_ctx, device, tp_rank, tp_size, out, err, errlen);
+}
+
+int b200_llama_tp_ipc_handle(const b200_llama *m, void *handle_out, size_t handle_bytes) {
+  if (!m || !handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) return B200_LLAMA_ERR_LOAD;
+  if (cudaSetDevice(m->device) != cudaSuccess) return B200_LLAMA_ERR_LOAD;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, m->d_xchg) != cudaSuccess) return B200_LLAMA_ERR_LOAD;
+  memcpy(handle_out, &h, sizeof(h));
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_tp_connect_ipc(b200_llama *m, const void *handles, size_t handle_stride, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_LOAD;
+  if (!m || !handles || handle_stride < sizeof(cudaIpcMemHandle_t)) { set_err(err, errlen, "null argument"); return fail_code; }
+  CUDA_TRY(cudaSetDevice(m->device));
+  for (int p = 0; p < m->tp_size; p++) {
+    if (p == m->tp_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const uint8_t *) handles + (size_t) p * handle_stride, sizeof(h));
+    void *ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    m->peer_xchg[p] = (uint8_t *) ptr;
+    m->peer_ipc[p] = true;
+  }
+  m->tp_connected = true;
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_load_group(const char *path, int n_ctx, const int *devices, int n_devices, b200_llama **out,
+                          char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_LOAD;
+  if (!out || !devices || n_devices < 1 || n_devices > MEGA_MAX_TP) { set_err(err, errlen, "bad device list"); return fail_code; }
+  *out = nullptr;
+  std::vector<b200_llama *> ms(n_devices, nullptr);
+  auto drop = [&]() { for (b200_llama *x : ms) free_model(x); };
+  for (int r = 0; r < n_devices; r++) {
+    const int rc = load_impl(path, n_ctx, devices[r], r, n_devices, &ms[r], err, errlen);
+    if (rc != B200_LLAMA_OK) { drop(); return rc; }
+  }
+  for (int r = 0; r < n_devices; r++) {
+    cudaError_t e = cudaSetDevice(devices[r]);
+    for (int p = 0; p < n_devices && e == cudaSuccess; p++) {
+      if (p == r) continue;
+      int can = 0;
+      e = cudaDeviceCanAccessPeer(&can, devices[r], devices[p]);
+      if (e == cudaSuccess && !can) { set_err(err, errlen, "device %d cannot access device %d (no NVLink / P2P)", devices[r], devices[p]); drop(); return fail_code; }
+      if (e == cudaSuccess) {
+        e = cudaDeviceEnablePeerAccess(devices[p], 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      }
+      ms[r]->peer_xchg[p] = ms[p]->d_xchg;
+    }
+    if (e != cudaSuccess) { set_err(err, errlen, "CUDA error %s while enabling peer access", cudaGetErrorString(e)); drop(); return fail_code; }
+    ms[r]->tp_connected = true;
+  }
+  ms[0]->group = ms;
+  *out = ms[0];
+  return B200_LLAMA_OK;
+}
+
+// The ranks of a single-process group (b200_llama_load_group) are driven by one host thread: everything that may
+// block or synchronise a device (allocation, blocking copies) happens BEFORE the first launch on any rank, then the
+// launches of all ranks are enqueued (asynchronous), then all streams are synchronised.  The token kernels of the
+// ranks wait for each other on the GPUs, never on the host.
+static std::vector<b200_llama *> ranks_of(b200_llama *m) {
+  return m->group.empty() ? std::vector<b200_llama *>{m} : m->group;
+}
+
+static int eval_enqueue(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  CUDA_TRY(cudaSetDevice(m->device));
+  m->last_launches = 0;
+  // The reference evaluates the N columns of every mat-mul independently, so the batch is run one token at a time;
+  // p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P partition, ggml.c:5628).
+  for (int i = 0; i < n_tokens; i++) {
+    set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, tokens[i], n_past + i, n_past + n_tokens, 0);
+    CUDA_TRY(cudaGetLastError());
+    m->last_launches++;
+    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
   return B200_LLAMA_OK;
 }
 
@@ -736,19 +905,65 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
   for (int i = 0; i < n_tokens; i++) {
     if (tokens[i] < 0 || tokens[i] >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", tokens[i]); return fail_code; }
   }
+  if (const char *why = tp_ready(m, n_threads)) { set_err(err, errlen, "%s", why); return fail_code; }
+  const std::vector<b200_llama *> ranks = ranks_of(m);
+  for (b200_llama *r : ranks) {
+    const int rc = eval_enqueue(r, n_threads, n_past, tokens, n_tokens, err, errlen);
+    if (rc != B200_LLAMA_OK) return rc;
+  }
+  for (b200_llama *r : ranks) {
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+  }
+  memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);      // every rank holds the full logits; the leader's are returned
+  return B200_LLAMA_OK;
+}
+
+static int decode_prepare(b200_llama *m, int n_steps, const int32_t *forced_tokens, bool want_logits, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (m->log_cap < n_steps) {
+    cudaFree(m->d_token_log); cudaFree(m->d_forced);
+    m->d_token_log = nullptr; m->d_forced = nullptr;
+    CUDA_TRY(cudaMalloc(&m->d_token_log, (size_t) n_steps * 4));
+    CUDA_TRY(cudaMalloc(&m->d_forced, (size_t) n_steps * 4));
+    m->log_cap = n_steps;
+  }
+  if (forced_tokens) CUDA_TRY(cudaMemcpy(m->d_forced, forced_tokens, (size_t) n_steps * 4, cudaMemcpyHostToDevice));
+  if (want_logits) {
+    const size_t need = (size_t) n_steps * m->n_vocab;
+    if (m->logits_log_cap < need) {
+      cudaFree(m->d_logits_log); m->d_logits_log = nullptr;
+      CUDA_TRY(cudaMalloc(&m->d_logits_log, need * 4));
+      m->logits_log_cap = need;
+    }
+  }
+  if (m->opt_time_kernel) {
+    while ((int) m->kev.size() < 2 * n_steps) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); m->kev.push_back(e); }
+  }
+  return B200_LLAMA_OK;
+}
+
+static int decode_enqueue(b200_llama *m, int n_threads, int n_past, int first_token, int n_steps, bool forced, bool want_logits,
+                          char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
   m->last_launches = 0;
-  // The reference evaluates the N columns of every mat-mul independently, so the batch is run one token at a time;
-  // p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P partition, ggml.c:5628).
-  for (int i = 0; i < n_tokens; i++) {
-    set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, tokens[i], n_past + i, n_past + n_tokens, 0);
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  for (int i = 0; i < n_steps; i++) {
+    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
+    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
+    if (want_logits) {
+      CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced ? m->d_forced : nullptr);
     CUDA_TRY(cudaGetLastError());
     m->last_launches++;
-    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
   }
-  CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
-  CUDA_TRY(cudaStreamSynchronize(m->stream));
-  memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
+  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
   return B200_LLAMA_OK;
 }
 
@@ -764,47 +979,26 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
   if (first_token < 0 || first_token >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", first_token); return fail_code; }
   if (n_threads < 1) n_threads = 1;
   if (n_threads > 64) { set_err(err, errlen, "n_threads %d > 64 not supported", n_threads); return fail_code; }
-  CUDA_TRY(cudaSetDevice(m->device));
-  if (m->log_cap < n_steps) {
-    cudaFree(m->d_token_log); cudaFree(m->d_forced);
-    m->d_token_log = nullptr; m->d_forced = nullptr;
-    CUDA_TRY(cudaMalloc(&m->d_token_log, (size_t) n_steps * 4));
-    CUDA_TRY(cudaMalloc(&m->d_forced, (size_t) n_steps * 4));
-    m->log_cap = n_steps;
-  }
   if (forced_tokens) {
     for (int i = 0; i < n_steps; i++)
       if (forced_tokens[i] < 0 || forced_tokens[i] >= m->n_vocab) { set_err(err, errlen, "token id %d out of range", forced_tokens[i]); return fail_code; }
-    CUDA_TRY(cudaMemcpyAsync(m->d_forced, forced_tokens, (size_t) n_steps * 4, cudaMemcpyHostToDevice, m->stream));
   }
-  if (logits_all) {
-    const size_t need = (size_t) n_steps * m->n_vocab;
-    if (m->logits_log_cap < need) {
-      cudaFree(m->d_logits_log); m->d_logits_log = nullptr;
-      CUDA_TRY(cudaMalloc(&m->d_logits_log, need * 4));
-      m->logits_log_cap = need;
-    }
+  if (const char *why = tp_ready(m, n_threads)) { set_err(err, errlen, "%s", why); return fail_code; }
+  const std::vector<b200_llama *> ranks = ranks_of(m);
+  for (b200_llama *r : ranks) {
+    r->opt_time_kernel = m->opt_time_kernel;
+    const int rc = decode_prepare(r, n_steps, forced_tokens, r == m && logits_all != nullptr, err, errlen);
+    if (rc != B200_LLAMA_OK) return rc;
   }
-  m->last_launches = 0;
-  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
-  if (m->opt_time_kernel) {
-    while ((int) m->kev.size() < 2 * n_steps) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); m->kev.push_back(e); }
+  for (b200_llama *r : ranks) {
+    const int rc = decode_enqueue(r, n_threads, n_past, first_token, n_steps, forced_tokens != nullptr, r == m && logits_all != nullptr, err, errlen);
+    if (rc != B200_LLAMA_OK) return rc;
   }
-  for (int i = 0; i < n_steps; i++) {
-    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
-    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
-    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
-    if (logits_all) {
-      CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
-    }
-    argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced_tokens ? m->d_forced : nullptr);
-    CUDA_TRY(cudaGetLastError());
-    m->last_launches++;
+  for (b200_llama *r : ranks) {
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
   }
-  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
-  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  CUDA_TRY(cudaSetDevice(m->device));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, m->ev0, m->ev1));
   if (m->opt_time_kernel) {
     m->last_kernel_ms = 0.0;
@@ -853,7 +1047,7 @@ long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes;
 /* Development profiler: run ONE token (current step scalars) through the whole-token kernel with per-CTA globaltimer
  * stamps at every phase boundary.  out receives n_cta * marks int64 nanosecond stamps; returns marks (or < 0). */
 int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta) {
-  if (!m || !mega_usable(m, n_threads)) return -1;
+  if (!m || !mega_usable(m, n_threads) || m->tp_size > 1) return -1;
   cudaSetDevice(m->device);
   const int marks = 2 + 15 * m->n_layer + 4;
   if ((long long) marks * m->n_sm > cap) return -2;
@@ -910,7 +1104,7 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
 #define MV_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e__), #expr); cleanup(); return fail_code; } } while (0)
   MV_TRY(configure_kernels());
   MV_TRY(cudaMalloc(&d_stage, t.data.size()));
-  MV_TRY(upload_matrix(&tmp, p, {&t}, 0, d_stage));
+  MV_TRY(upload_matrix(&tmp, p, {RowSlice{t.data.data(), t.data.size()}}, 0, d_stage));
   MV_TRY(cudaMalloc(&d_x, (size_t) K * 4));
   MV_TRY(cudaMalloc(&d_out, (size_t) M * 4));
   MV_TRY(cudaMemcpy(d_x, x, (size_t) K * 4, cudaMemcpyHostToDevice));

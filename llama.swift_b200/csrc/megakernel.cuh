@@ -1,16 +1,19 @@
 // decode_token_kernel: one persistent launch evaluates one token through the whole network (llama_eval with N = 1,
 // PO.mm:510-735).  It replaces ggml_graph_compute's thread pool (ggml.c:9109-9555) with a B200-shaped schedule:
 //
-//   * grid = one CTA per SM (148), co-resident (cooperative launch): 14 compute warps, 1 TMA loader warp and
-//     1 L2-prefetch warp each;
+//   * grid = one CTA per SM (148), co-resident (cooperative launch): 16 compute warps + 1 TMA loader warp each;
 //   * every Q4_0 weight byte of the token (4.13 GB at 7B) is streamed exactly once through a per-CTA ring of
 //     shared-memory stages by cp.async.bulk (1-D TMA).  The loader walks the static schedule
 //     layer0.{wq|wk|wv, wo, w1|w3, w2}, layer1..., output and runs AHEAD of the compute warps across phase boundaries
-//     by up to the ring capacity (~170 KB/SM, ~25 MB chip-wide); the prefetch warp runs further ahead still and pulls
-//     the next ~50 MB of the stream from HBM into L2 (cp.async.bulk.prefetch.L2), so HBM keeps streaming while the
-//     compute warps sit in a grid barrier, a LayerNorm prologue or the attention phase;
-//   * five grid barriers per layer (qkv | attention | wo | w1w3 | w2) are the only synchronisation; activations
-//     cross them through L2 (ld.global.cg), never through stale L1 lines.
+//     by up to the ring capacity (~190 KB/SM, ~28 MB chip-wide), so HBM keeps streaming while the compute warps wait
+//     for activations, run a LayerNorm prologue or the attention phase;
+//   * activations travel as FLAGGED words: every f32 is stored as an 8-byte {value, sequence} pair (one
+//     st.volatile.v2 -- single-copy atomic) and the consumer's prologue polls the words it needs until the sequence
+//     number of (token, layer) shows up.  Data and "ready" signal arrive in ONE store, so four of the five
+//     grid-wide barriers per layer of a conventional schedule disappear (only qkv -> attention keeps a counter
+//     barrier, because attention reads the plain f32 KV cache);
+//   * the same stores go to every GPU of a tensor-parallel group through peer-mapped memory (NVLink 5 / NVSwitch):
+//     the all-gather of finished activation slices IS the epilogue -- no NCCL call, no separate collective kernel.
 //
 // The arithmetic is the same operation-for-operation mirror of the reference's AVX2 build as kernels.cuh (the
 // per-matrix kernels kept for A/B and for reference thread counts > 16): see the contract there.  -fmad=false.
@@ -36,6 +39,19 @@ struct LayerDesc {
 };
 
 constexpr int MEGA_MAX_LAYERS = 80;   // LLaMA-65B; the descriptors ride in the (large, CUDA >= 12.1) kernel parameter block
+constexpr int MEGA_MAX_TP = 8;        // GPUs of one NVSwitch box
+
+// Tensor-parallel group.  Every matrix is split by ROWS over the ranks (wq/wk/wv by head), so
+// each rank evaluates complete reference dot products -- the same operations in the same order as the unsharded
+// reference, bit for bit -- and what crosses NVLink are finished activation slices (an all-gather by peer stores),
+// never partial sums.  size == 1 is the single-GPU case and uses the very same code path with one "peer".
+struct TpArgs {
+  int rank, size;
+  int e_loc, f_loc, v_loc;            // this rank's share of n_embd (rows of wq|wk|wv|wo|w2 = its heads), n_ff, n_vocab
+  uint2 *ll[MEGA_MAX_TP];             // peer p's flagged activation area (p == rank: the local one)
+  float *logits[MEGA_MAX_TP];         // peer p's logits vector [n_vocab]
+  unsigned int *done[MEGA_MAX_TP];    // peer p's end-of-token flags [size]
+};
 
 struct TokenArgs {
   LayerDesc layers[MEGA_MAX_LAYERS];   // in the constant bank: descriptor fields cost no registers and no loads
@@ -43,11 +59,14 @@ struct TokenArgs {
   MatDesc out;
   const float *final_norm;
   const uint8_t *tok_emb;
-  float *inpL, *inpFF, *q, *att, *h, *logits;
+  float *q;                 // roped Q of this token [n_embd] (rank-local: only this rank's heads are used)
+  TpArgs tp;
+  unsigned int *epoch;      // launch counter in HBM (>= 1): makes every flag value of every token unique
+  long long spin_limit;     // clock64 ticks before a spin-wait traps instead of hanging the box
   const double2 *rope;
   const uint16_t *silu_table, *exp_table;
   const StepParams *sp;
-  unsigned int *bar;        // grid-barrier counter, zeroed before every launch
+  unsigned int *bar;        // [0] grid-barrier counter, [1] end-of-token CTA counter; zeroed before every launch
   int n_embd, n_head, n_ctx, n_ff, n_threads;
   float kq_scale;
   int S, stage_bytes;
@@ -83,10 +102,48 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// Grid barrier for the compute warps (the loader / prefetch warps never join: they only obey the ring).
+// ---- flagged activation words ("LL" protocol: value and ready-flag in one 8-byte single-copy-atomic store) -----------
+__device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 ld_vol_v2(const void *p) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_vol_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void ll_store(uint2 *p, float v, uint32_t seq) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+// one flagged word: spin until its sequence number is `seq`
+__device__ __forceinline__ float ll_wait1(const uint2 *p, uint32_t seq, long long limit) {
+  uint2 r = ld_vol_v2(p);
+  if (r.y != seq) {
+    const long long t0 = clock64();
+    do {
+      r = ld_vol_v2(p);
+      if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+    } while (r.y != seq);
+  }
+  return __uint_as_float(r.x);
+}
+
+struct TokenArgs;
+// store one activation value into the flagged area of every GPU of the group (the local one included)
+__device__ __forceinline__ void ll_bcast(uint2 *const (&ll)[MEGA_MAX_TP], int n_peers, uint32_t off, float v, uint32_t seq) {
+  for (int p = 0; p < n_peers; p++) ll_store(ll[p] + off, v, seq);
+}
+
+// Grid barrier for the compute warps (the loader warp never joins: it only obeys the ring).
 // bar.sync orders every compute thread's global writes before thread 0's gpu-scope release; the acquire + bar.sync
-// order every later ld.global.cg after the other CTAs' releases.
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &phase, int tid) {
+// order every later global read after the other CTAs' releases.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &phase, int tid, long long limit) {
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
   phase++;
   if (tid == 0) {
@@ -95,7 +152,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ph
     if (ld_acquire_u32(bar) < target) {
       const long long t0 = clock64();
       while (ld_acquire_u32(bar) < target) {
-        if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }   // never hang the box
+        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
       }
     }
   }
@@ -184,36 +241,64 @@ __device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s
 }
 
 // ---- activation prologues ------------------------------------------------------------------------------------------
-// PLAIN: quantize x[K] (global, read through L2) -> xq/dxs.  An "item" is 8 consecutive floats = a quarter block.
-template <int ROUNDS>
-__device__ __forceinline__ void prologue_plain_r(const float *x, int items, const MegaSmem &sm, int tid) {
-  float4 va[ROUNDS], vc[ROUNDS];
+// An "item" is 8 consecutive activation values = a quarter of a Q4 block = 4 x 16 bytes of flagged words.
+// Read N rounds of items (item it0 + tid + rd*512 in round rd): all loads are issued before the first flag is
+// checked (one L2 latency when the data is already there), then every 16-byte half-pair is re-polled until both of its
+// sequence numbers match.  Threads past the end re-read the last item (harmless duplicates).
+template <int N>
+__device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int it0, uint32_t seq, long long limit,
+                                               float (&v)[N][8], int tid) {
+  uint4 r[N][4];
 #pragma unroll
-  for (int rd = 0; rd < ROUNDS; rd++) {   // every round's loads are in flight before the first quantize: one L2 latency
-    const int it = min(tid + rd * MEGA_COMPUTE_THREADS, items - 1);
-    va[rd] = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2);
-    vc[rd] = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2 + 1);
+  for (int rd = 0; rd < N; rd++) {
+    const int it = min(it0 + tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t) it * 8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[rd][i] = ld_vol_v4(p + i);
   }
 #pragma unroll
-  for (int rd = 0; rd < ROUNDS; rd++) {
-    const int it = tid + rd * MEGA_COMPUTE_THREADS;
-    const bool live = it < items;         // a block's 4 quarter-items are all live or all padding (512 % 4 == 0)
-    const int iq = live ? it : items - 1;
-    const float v[8] = {va[rd].x, va[rd].y, va[rd].z, va[rd].w, vc[rd].x, vc[rd].y, vc[rd].z, vc[rd].w};
-    quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+  for (int rd = 0; rd < N; rd++) {
+    const int it = min(it0 + tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t) it * 8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (r[rd][i].y != seq || r[rd][i].w != seq) {
+        const long long t0 = clock64();
+        do {
+          r[rd][i] = ld_vol_v4(p + i);
+          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+        } while (r[rd][i].y != seq || r[rd][i].w != seq);
+      }
+      v[rd][2 * i] = __uint_as_float(r[rd][i].x);
+      v[rd][2 * i + 1] = __uint_as_float(r[rd][i].z);
+    }
   }
 }
 
-__device__ __forceinline__ void prologue_plain(const float *x, int nb, const MegaSmem &sm, int tid) {
+// PLAIN: quantize x[K] (flagged words, polled) -> xq/dxs.
+template <int N>
+__device__ __forceinline__ void prologue_plain_batch(const uint2 *src, int items, int it0, uint32_t seq, long long limit,
+                                                     const MegaSmem &sm, int tid) {
+  float v[N][8];
+  ll_read_rounds<N>(src, items, it0, seq, limit, v, tid);
+#pragma unroll
+  for (int rd = 0; rd < N; rd++) {
+    const int it = it0 + tid + rd * MEGA_COMPUTE_THREADS;
+    const bool live = it < items;         // a block's 4 quarter-items are all live or all padding (512 % 4 == 0)
+    const int iq = live ? it : items - 1;
+    quantize_block_4t(v[rd], iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+  }
+}
+
+__device__ __forceinline__ void prologue_plain(const uint2 *src, int nb, uint32_t seq, long long limit, const MegaSmem &sm, int tid) {
   const int items = nb * 4;
   const int rounds = (items + MEGA_COMPUTE_THREADS - 1) / MEGA_COMPUTE_THREADS;
-  switch (rounds) {
-    case 1: prologue_plain_r<1>(x, items, sm, tid); break;
-    case 2: prologue_plain_r<2>(x, items, sm, tid); break;
-    case 3: prologue_plain_r<3>(x, items, sm, tid); break;
-    case 4: prologue_plain_r<4>(x, items, sm, tid); break;
-    case 5: prologue_plain_r<5>(x, items, sm, tid); break;
-    default: prologue_plain_r<6>(x, items, sm, tid); break;   // K <= 24576 (the host refuses larger n_ff for this kernel)
+  for (int r0 = 0; r0 < rounds; r0 += 3) {     // at most 3 rounds (12 x 16 B per thread) in flight at a time
+    const int n = rounds - r0;
+    const int it0 = r0 * MEGA_COMPUTE_THREADS;
+    if (n >= 3) prologue_plain_batch<3>(src, items, it0, seq, limit, sm, tid);
+    else if (n == 2) prologue_plain_batch<2>(src, items, it0, seq, limit, sm, tid);
+    else prologue_plain_batch<1>(src, items, it0, seq, limit, sm, tid);
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
@@ -274,21 +359,24 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
-// fill the register copy of a global f32 vector (through L2)
-__device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], const float *x, int nb, int tid) {
+// fill the register copy of a flagged activation vector (polled)
+__device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], const uint2 *src, int nb, uint32_t seq,
+                                           long long limit, int tid) {
   const int items = nb * 4;
+  float v[MEGA_NORM_ROUNDS][8];
+  if (items <= MEGA_COMPUTE_THREADS) {
+    float v1[1][8];
+    ll_read_rounds<1>(src, items, 0, seq, limit, v1, tid);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v[0][i] = v1[0][i]; v[1][i] = 0.0f; }
+  } else {
+    ll_read_rounds<MEGA_NORM_ROUNDS>(src, items, 0, seq, limit, v, tid);
+  }
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
-    const int it = tid + rd * MEGA_COMPUTE_THREADS;
-    if (it < items) {
-      const float4 a = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2);
-      const float4 c = __ldcg(reinterpret_cast<const float4 *>(x) + it * 2 + 1);
-      xd[rd][0] = a.x; xd[rd][1] = a.y; xd[rd][2] = a.z; xd[rd][3] = a.w;
-      xd[rd][4] = c.x; xd[rd][5] = c.y; xd[rd][6] = c.z; xd[rd][7] = c.w;
-    } else {
+    const bool live = tid + rd * MEGA_COMPUTE_THREADS < items;
 #pragma unroll
-      for (int i = 0; i < 8; i++) xd[rd][i] = 0.0;
-    }
+    for (int i = 0; i < 8; i++) xd[rd][i] = live ? (double) v[rd][i] : 0.0;
   }
 }
 
@@ -304,6 +392,54 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 #ifndef B200_NO_MATH
 #define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
 #endif
+
+#ifndef B200_PIPE
+#define B200_PIPE 1         // 1: software-pipelined row loop (loads of group g+1 in flight under the math of group g)
+#endif
+
+// Operands of U consecutive blocks of one row (LP lane pairs each), held in registers.
+template <int LP, int U>
+struct BlkRegs {
+  uint32_t w[U][LP];
+  uint4 x[U][LP];
+  float sc[U], dx[U];
+};
+
+template <int LP, int U>
+__device__ __forceinline__ void blk_load(BlkRegs<LP, U> &b, const uint32_t *pw, const float *ps, const uint4 *px,
+                                         const float *pd, int wstride, int R) {
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    if constexpr (LP == 4) {
+      const uint4 t = *reinterpret_cast<const uint4 *>(pw + u * wstride);
+      b.w[u][0] = t.x; b.w[u][1] = t.y; b.w[u][2] = t.z; b.w[u][3] = t.w;
+    } else if constexpr (LP == 2) {
+      const uint2 t = *reinterpret_cast<const uint2 *>(pw + u * wstride);
+      b.w[u][0] = t.x; b.w[u][1] = t.y;
+    } else {
+      b.w[u][0] = pw[u * wstride];
+    }
+    b.sc[u] = ps[u * R];
+    b.dx[u] = pd[u];
+#pragma unroll
+    for (int j = 0; j < LP; j++) b.x[u][j] = px[u * 4 + j];
+  }
+}
+
+template <int LP, int U>
+__device__ __forceinline__ void blk_math(const BlkRegs<LP, U> &b, u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const float sdx = __fmul_rn(b.sc[u], b.dx[u]);                               // _mm256_mul_ps(d0, d1), ggml.c:1431
+#pragma unroll
+    for (int j = 0; j < LP; j++) {
+      const int ia = dp4a_us(b.w[u][j] & 0x0F0F0F0Fu, (int) b.x[u][j].x, (int) b.x[u][j].z);   // float bits of 12582912 + isum(lane 2p)
+      const int ib = dp4a_us(b.w[u][j] & 0xF0F0F0F0u, (int) b.x[u][j].y, (int) b.x[u][j].w);   // float bits of 12582912 + 16*isum(lane 2p+1)
+      const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                   // exact (float)isum for both lanes
+      acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                             // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+    }
+  }
+}
 
 // Position in the ring of stages: stage index and the parity of its mbarrier phase, advanced without div/mod.
 struct RingPos {
@@ -348,6 +484,32 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
       const uint4 *px = sm.xq + k * cb * 4 + pg * LP;
       const float *pd = sm.dxs + k * cb;
       int bl = 0;
+#if B200_PIPE
+      {
+        // Software pipeline over groups of U blocks with two register sets: the shared-memory loads of the next group
+        // are issued before the math of the current one, so the only serial dependence left per block is the
+        // reference's own accumulator FMA.  The look-ahead may read up to 2 groups past the end of the chunk: those
+        // addresses are still inside this CTA's shared memory and the values are never used.
+        constexpr int U = LP == 1 ? 4 : (LP == 2 ? 2 : 1);
+        const int ng = cbk / U;
+        BlkRegs<LP, U> ra, rb;
+        blk_load<LP, U>(ra, pw, ps, px, pd, wstride, R);
+        int g = 0;
+        for (; g + 2 <= ng; g += 2) {
+          blk_load<LP, U>(rb, pw + U * wstride, ps + U * R, px + U * 4, pd + U, wstride, R);
+          blk_math<LP, U>(ra, acc, cvt_mul, cvt_sub);
+          blk_load<LP, U>(ra, pw + 2 * U * wstride, ps + 2 * U * R, px + 2 * U * 4, pd + 2 * U, wstride, R);
+          blk_math<LP, U>(rb, acc, cvt_mul, cvt_sub);
+          pw += 2 * U * wstride; ps += 2 * U * R; px += 2 * U * 4; pd += 2 * U;
+        }
+        if (g < ng) {
+          blk_math<LP, U>(ra, acc, cvt_mul, cvt_sub);
+          pw += U * wstride; ps += U * R; px += U * 4; pd += U;
+          g++;
+        }
+        bl = g * U;
+      }
+#endif
 #if B200_ROWLOOP
       constexpr int U = LP == 1 ? 8 : (LP == 2 ? 4 : 2);
       for (; bl + U <= cbk; bl += U) {
@@ -549,7 +711,7 @@ __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart r
 
 // ---- attention phase for (head h, output quarter qr): K.Q for all positions, soft_max, V.P for 32 dims --------------
 __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerDesc &L, const MegaSmem &sm, int h, int qr,
-                                                int pos, int p_part, int tid) {
+                                                int pos, int p_part, uint32_t att_off, uint32_t seq, int tid) {
   constexpr int HD = 128, NW = MEGA_COMPUTE_WARPS;
   const int lane = tid & 31, warp = tid >> 5;
   const int E = a.n_embd;
@@ -653,7 +815,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   if (warp == 0) {
     float o = sm.part[lane];
     for (int t = 1; t < nth; t++) o = __fadd_rn(o, sm.part[t * 32 + lane]);
-    a.att[h * HD + qr * 32 + lane] = o;                                           // KQV_merged, PO.mm:641-646
+    ll_bcast(a.tp.ll, a.tp.size, att_off + h * HD + qr * 32 + lane, o, seq);      // KQV_merged, PO.mm:641-646 -> every GPU
   }
 }
 
@@ -739,7 +901,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 #else
             // g.par is the parity of the fill about to start; the slot is free once the consumers released the
             // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
-            mbar_wait(&sm.empty[s], g.par ^ 1u);
+            mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
 #endif
             const int cbk = min(md.cb, md.nb - k * md.cb);
             const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
@@ -773,10 +935,23 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
   // ===== compute warps =====
   // ONE loop over the token's phases with a single instance of the row loops: the kind of phase only selects the
-  // prologue (how the activation vector is produced and quantized) and the epilogue (the graph nodes that consume the
+  // prologue (how the activation vector is obtained and quantized) and the epilogue (the graph nodes that consume the
   // mat-vec).  Descriptors come from the kernel parameter block (constant bank).
-  const int E = a.n_embd, HD = E / a.n_head;
+  const int E = a.n_embd, HD = E / a.n_head, F = a.n_ff;
+  const int T = a.tp.size, rank = a.tp.rank;
+  const int e_loc = a.tp.e_loc, f_loc = a.tp.f_loc, v_loc = a.tp.v_loc;
+  const int c0 = rank * e_loc;                        // first n_embd index (q/k/v column, wo/w2 row) owned by this rank
+  const int nh_loc = a.n_head / T;
+  const long long limit = a.spin_limit;
   const int pos = a.sp->pos;
+  // flag values: the input of layer l of THIS launch carries seq0 + l (att / inpFF / h of layer l too, in their own
+  // buffers); epoch >= 1 and never repeats, so a stale word of an earlier token can never match
+  const uint32_t epoch = ld_vol_u32(a.epoch);
+  const uint32_t seq0 = epoch * (uint32_t) (a.n_layer + 2) + 1u;
+  // flagged area (uint2 units): inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F]; the buffer alternates with the layer
+  // parity so a fast producer of layer l+1 can never overwrite words a slow consumer of layer l still polls
+  const uint32_t o_inpL = 0u, o_inpFF = 2u * E, o_att = 4u * E, o_h = 6u * E;
+  uint2 *const ll_me = a.tp.ll[rank];
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
   unsigned int phase = 0;
@@ -787,22 +962,31 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const int il = step / 5;
     const int kind = il < a.n_layer ? step - 5 * il : PH_OUT;
     const LayerDesc &L = a.layers[il < a.n_layer ? il : 0];
+    const uint32_t seq = seq0 + (uint32_t) il;
+    const uint32_t par = (uint32_t) il & 1u;
 
     if (kind == PH_ATTN) {
-      // ---- attention (PO.mm:614-646) on the first 4*n_head CTAs ----
-      if ((int) blockIdx.x < 4 * a.n_head) attention_phase(a, L, sm, blockIdx.x >> 2, blockIdx.x & 3, pos, a.sp->p_part, tid);
+      // ---- attention (PO.mm:614-646): this rank's heads, 4 CTAs per head; the result goes to every GPU ----
+      if ((int) blockIdx.x < 4 * nh_loc)
+        attention_phase(a, L, sm, rank * nh_loc + (blockIdx.x >> 2), blockIdx.x & 3, pos, a.sp->p_part, o_att + par * E, seq, tid);
       PROF_MARK();
-      grid_barrier(a.bar, phase, tid);
-      PROF_MARK();
+      continue;      // no barrier: the consumers poll the flagged words
+    }
+
+    const MatDesc &md = kind == PH_QKV ? L.qkv : kind == PH_WO ? L.wo : kind == PH_W13 ? L.w13 : kind == PH_W2 ? L.w2 : a.out;
+    const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
+    if (rp.R == 0) {
+      // no rows of this matrix on this CTA (tensor-parallel shards can have fewer row granules than SMs)
+      PROF_MARK(); PROF_MARK(); PROF_MARK();
+      if (kind == PH_QKV) { grid_barrier(a.bar, phase, tid, limit); PROF_MARK(); }
       continue;
     }
 
     // ---- prologue ----
-    const MatDesc &md = kind == PH_QKV ? L.qkv : kind == PH_WO ? L.wo : kind == PH_W13 ? L.w13 : kind == PH_W2 ? L.w2 : a.out;
     if (kind == PH_WO) {
-      prologue_plain(a.att, E / 32, sm, tid);                                   // PO.mm:649-651
+      prologue_plain(ll_me + o_att + par * E, E / 32, seq, limit, sm, tid);     // PO.mm:649-651
     } else if (kind == PH_W2) {
-      prologue_plain(a.h, a.n_ff / 32, sm, tid);                                // PO.mm:682-684
+      prologue_plain(ll_me + o_h + par * F, F / 32, seq, limit, sm, tid);       // PO.mm:682-684
     } else {
       double xd[MEGA_NORM_ROUNDS][8];
       if (step == 0) {
@@ -821,7 +1005,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
               const int qn = (by >> (4 * i)) & 0xf;             // element 2j = low nibble of byte j, 2j+1 = high nibble
               const float v = __fmul_rn((float) (qn - 8), d);
               xd[rd][i] = v;
-              if (blockIdx.x == 0) a.inpL[it * 8 + i] = v;      // residual source for layer 0 (read after two grid barriers)
+              if (blockIdx.x == 0) ll_store(ll_me + o_inpL + it * 8 + i, v, seq0);   // residual source of layer 0 (this GPU only)
             }
           } else {
 #pragma unroll
@@ -829,7 +1013,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           }
         }
       } else {
-        load_items(xd, kind == PH_W13 ? a.inpFF : a.inpL, E / 32, tid);
+        load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, E / 32, seq, limit, tid);
       }
       const float *nw = kind == PH_QKV ? L.attn_norm : kind == PH_W13 ? L.ffn_norm : a.final_norm;
       prologue_norm_regs(xd, nw, E / 32, sm, tid);                              // PO.mm:570-575, 660-665, 694-701
@@ -837,17 +1021,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     PROF_MARK();
 
     // ---- the mat-vec ----
-    const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
     gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, a.split_rows, tid);
     PROF_MARK();
 
     // ---- epilogue ----
     if (kind == PH_QKV) {
-      // rope (ggml.c:7110-7127, double math, host-built angles) + KV store (PO.mm:585-611)
+      // fused local rows [0,e_loc) = wq, [e_loc,2e_loc) = wk, [2e_loc,3e_loc) = wv of this rank's heads.
+      // rope (ggml.c:7110-7127, double math, host-built angles) + KV store (PO.mm:585-611); all rank-local
       for (int i = tid; i < rp.R / 2; i += MEGA_COMPUTE_THREADS) {
         const int g = rp.row0 + 2 * i;
         if (g >= md.M) continue;
-        const int which = g / E, col = g - which * E;
+        const int which = g / e_loc, col = c0 + (g - which * e_loc);
         float y0 = sm.rowres[2 * i], y1 = sm.rowres[2 * i + 1];
         if (which < 2) {
           const double2 cs = sm.ropev[(col % HD) / 2];
@@ -860,6 +1044,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         dst[1] = y1;
       }
       PROF_MARK();
+      grid_barrier(a.bar, phase, tid, limit);     // attention reads plain f32 (q, the K/V cache rows): counter barrier
     } else if (kind == PH_W13) {
       // fused rows 2i = w1 row i, 2i+1 = w3 row i: silu(w1 x) * (w3 x), PO.mm:678-680; silu via the fp16 table (ggml.c:1955-1963)
       for (int i = tid; i < rp.R / 2; i += MEGA_COMPUTE_THREADS) {
@@ -867,20 +1052,62 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         if (2 * g < md.M) {
           const uint16_t hx = __half_as_ushort(__float2half_rn(sm.rowres[2 * i]));
           const float sv = __half2float(__ushort_as_half(__ldg(a.silu_table + hx)));
-          a.h[g] = __fmul_rn(sv, sm.rowres[2 * i + 1]);
+          ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, __fmul_rn(sv, sm.rowres[2 * i + 1]), seq);
+        }
+      }
+    } else if (kind == PH_OUT) {
+      // the plain logits (PO.mm:705); every GPU of the group receives the full vector
+      for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
+        const int g = rp.row0 + i;
+        if (g < md.M) {
+          const float v = sm.rowres[i];
+          for (int p = 0; p < T; p++) a.tp.logits[p][rank * v_loc + g] = v;
         }
       }
     } else {
-      // ggml_add with the residual stream (PO.mm:654, 687), or the plain logits store (PO.mm:705)
-      const float *resid = kind == PH_WO ? a.inpL : a.inpFF;
-      float *dst = kind == PH_WO ? a.inpFF : kind == PH_W2 ? a.inpL : a.logits;
+      // ggml_add with the residual stream (PO.mm:654, 687).  wo: inpFF(l) = wo.att + inpL(l); w2: inpL(l+1) = w2.h + inpFF(l).
+      // The residual words were validated by this CTA's own earlier prologue; the poll is a formality.
+      const uint32_t o_res = (kind == PH_WO ? o_inpL : o_inpFF) + par * E;
+      const uint32_t o_dst = kind == PH_WO ? o_inpFF + par * E : o_inpL + (par ^ 1u) * E;
+      const uint32_t seq_dst = kind == PH_WO ? seq : seq + 1u;
       for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
         const int g = rp.row0 + i;
-        if (g < md.M) dst[g] = kind == PH_OUT ? sm.rowres[i] : __fadd_rn(sm.rowres[i], __ldcg(resid + g));
+        if (g < md.M) {
+          const float r = ll_wait1(ll_me + o_res + c0 + g, seq, limit);
+          ll_bcast(a.tp.ll, T, o_dst + c0 + g, __fadd_rn(sm.rowres[i], r), seq_dst);
+        }
       }
     }
-    if (kind != PH_OUT) grid_barrier(a.bar, phase, tid);
     PROF_MARK();
+  }
+
+  // ---- end of token ----
+  if (T > 1) {
+    // The next kernel on this stream (arg-max, the D2H copy of the logits) must see every peer's logits stores: each CTA
+    // fences its own peer stores system-wide, the last CTA of this GPU then tells every peer "rank r finished token
+    // `epoch`" and waits until all peers said the same.  The kernel cannot complete before that CTA does.
+    named_bar_sync(1, MEGA_COMPUTE_THREADS);
+    if (tid == 0) {
+      __threadfence_system();
+      const unsigned int old = atomicAdd(a.bar + 1, 1u);
+      if (old == gridDim.x - 1) {
+        __threadfence_system();
+        for (int p = 0; p < T; p++)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.tp.done[p] + rank), "r"(epoch) : "memory");
+        for (int q = 0; q < T; q++) {
+          const long long t0 = clock64();
+          for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tp.done[rank] + q) : "memory");
+            if ((int) (v - epoch) >= 0) break;
+            if (clock64() - t0 > limit) { asm volatile("trap;"); }
+          }
+        }
+        *a.epoch = epoch + 1u;
+      }
+    }
+  } else if (blockIdx.x == 0 && tid == 0) {
+    *a.epoch = epoch + 1u;       // every CTA read the old value before CTA 0 can get here (it needed their rows)
   }
 }
 

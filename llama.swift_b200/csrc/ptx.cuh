@@ -51,11 +51,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a lost arrival must never hang the GPU box -- trap after ~2 s instead.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, long long limit = 4000000000LL) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+    if (clock64() - t0 > limit) { asm volatile("trap;"); }
   }
 }
 // 1-D bulk async copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)

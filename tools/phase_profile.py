@@ -33,22 +33,25 @@ for rep in range(3):
 assert marks > 0, marks
 t = buf[: ncta.value * marks].reshape(ncta.value, marks).astype(np.float64)
 t = (t - t[:, 0].min()) / 1e3   # us
-names = ["qkv prologue", "qkv rows", "qkv epilogue", "barrier1", "attention", "barrier2", "wo prologue", "wo rows",
-         "wo epi+barrier3", "w13 prologue", "w13 rows", "w13 epi+barrier4", "w2 prologue", "w2 rows", "w2 epi+barrier5"]
+# marks per layer (megakernel.cuh): qkv {prologue = wait for inpL + LayerNorm + quantize, rows, epilogue, local barrier},
+# attention, then {prologue = wait for the flagged activation words + quantize, rows, epilogue = flagged stores} x 3
+names = ["qkv wait+norm+quant", "qkv rows", "qkv epilogue", "barrier (qkv->attn)", "attention", "wo wait+quant", "wo rows",
+         "wo epilogue", "w13 wait+norm+quant", "w13 rows", "w13 epilogue", "w2 wait+quant", "w2 rows", "w2 epilogue"]
+NM = len(names)
 nl = args.layers
-print(f"layers {nl} pos {args.pos}: kernel span {t[:, 15 * nl + 3].max():.1f} us; "
-      f"per layer {(t[:, 15 * nl].max() - t[:, 0].min()) / nl:.2f} us")
-seg = np.zeros((nl, 15, ncta.value))
+print(f"layers {nl} pos {args.pos}: kernel span {t[:, NM * nl + 3].max():.1f} us; "
+      f"per layer {(t[:, NM * nl].max() - t[:, 0].min()) / nl:.2f} us")
+seg = np.zeros((nl, NM, ncta.value))
 for il in range(nl):
-    for k in range(15):
-        seg[il, k] = t[:, 15 * il + k + 1] - t[:, 15 * il + k]
+    for k in range(NM):
+        seg[il, k] = t[:, NM * il + k + 1] - t[:, NM * il + k]
 for k, n in enumerate(names):
     med = np.median(seg[1:, k, :])
     mx = np.mean(np.max(seg[1:, k, :], axis=1))
     mn = np.mean(np.min(seg[1:, k, :], axis=1))
-    print(f"{n:>18}: median CTA {med:6.2f} us   slowest CTA {mx:6.2f} us   fastest {mn:6.2f} us")
-print(f"{'sum of medians':>18}: {sum(np.median(seg[1:, k, :]) for k in range(15)):.2f} us/layer")
-o = 15 * nl
+    print(f"{n:>22}: median CTA {med:6.2f} us   slowest CTA {mx:6.2f} us   fastest {mn:6.2f} us")
+print(f"{'sum of medians':>22}: {sum(np.median(seg[1:, k, :]) for k in range(NM)):.2f} us/layer")
+o = NM * nl
 print(f"output: prologue {np.median(t[:, o + 1] - t[:, o]):.2f}  rows {np.median(t[:, o + 2] - t[:, o + 1]):.2f}  store {np.median(t[:, o + 3] - t[:, o + 2]):.2f} us (median CTA)")
 if args.out:
     np.save(args.out, t)
