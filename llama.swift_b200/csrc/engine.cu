@@ -54,7 +54,6 @@ void set_err(char *err, size_t errlen, const char *fmt, ...) {
 
 struct GemvPlan {
   int qtype = 2;            // 2 = Q4_0 (20 B / 32 weights), 3 = Q4_1 (24 B / 32 weights)
-  int split = 0;            // whole-token kernel runs this matrix in producer/chain mode
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
   int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
@@ -98,23 +97,20 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   }
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
-  // one ring-stage holds one chunk in both the per-matrix kernels and the whole-token kernel
-  p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 20)));
-  const int batch = lp == 1 ? 8 : (lp == 2 ? 4 : 2);     // blocks whose loads the row loop issues together
-  if (p.cb >= batch) p.cb -= p.cb % batch;
-  // small matrices: producer/chain row loop of the whole-token kernel (hands over SPLIT_SB blocks at a time)
-  if (env_int("B200_SPLIT", 0) && p.rmax * 4 <= 128 && p.nb % SPLIT_SB == 0 && p.cb >= SPLIT_SB) {
-    p.split = 1;
-    p.cb -= p.cb % SPLIT_SB;
-  }
-  p.stage_bytes = (p.cb * p.rmax * 20 + 127) & ~127;
-  const int nchunks = (p.nb + p.cb - 1) / p.cb;
-  const size_t fixed = (size_t) p.nb * 64 + (size_t) ((p.nb + 3) & ~3) * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
-  int S = (int) ((kSmemBudget - fixed - 256) / (p.stage_bytes + 16));
+  // One ring stage holds one chunk of whole quads (4 blocks x rmax rows x 80 B) in both the per-matrix kernels and the
+  // whole-token kernel; an even number of quads per chunk where possible (the LP = 1 row loop works on quad pairs).
+  const int nbq = (p.nb + 3) / 4;
+  int cq = std::max(1, std::min(nbq, stage_bytes_cfg() / (p.rmax * 80)));
+  if (cq >= 2) cq -= cq % 2;
+  p.cb = cq * 4;
+  p.stage_bytes = (cq * p.rmax * 80 + 127) & ~127;
+  const int nchunks = (nbq + cq - 1) / cq;
+  const size_t fixed = (size_t) nbq * 4 * 64 + (size_t) nbq * 4 * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+  int S = (int) ((kSmemBudget - (long) fixed - 256) / (p.stage_bytes + 16));
   S = std::max(1, std::min(S, nchunks));
   p.S = S;
   p.smem = (size_t) S * p.stage_bytes + fixed + (size_t) 2 * S * 8;
-  p.bytes = (size_t) p.g_total * 4 * p.nb * 20;
+  p.bytes = (size_t) p.g_total * 4 * nbq * 80;
   return p;
 }
 
@@ -248,7 +244,7 @@ struct b200_llama {
   int prof_marks = 0;
   TokenArgs *h_token_args = nullptr;   // host copy of the kernel parameter block (layer descriptors prefilled)
   unsigned int *d_bar = nullptr;
-  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0, mega_split_rows = 0;
+  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
   size_t mega_smem = 0;
 
   // tensor-parallel group: this handle is rank tp_rank of tp_size; every matrix is split by rows
@@ -279,7 +275,7 @@ int attn_smem_bytes(const b200_llama *m, int n_threads) {
 // One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
 MatDesc mat_desc(const GemvPlan &p) {
   MatDesc d = {};
-  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.pad = p.split;
+  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.pad = 0;
   return d;
 }
 
@@ -309,7 +305,6 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
-  a.split_rows = m->mega_split_rows;
   a.prof = m->d_prof; a.prof_marks = m->prof_marks;
   a.l2_ahead = m->opt_l2_ahead;
   cudaLaunchConfig_t cfg = {};
@@ -433,14 +428,16 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice
     if (e != cudaSuccess) return e;
     off += t.bytes;
   }
-  const long long total = (long long) p.g_total * 4 * p.nb;
   const int threads = 256;
-  if (p.qtype == 3)
+  if (p.qtype == 3) {
+    const long long total = (long long) p.g_total * 4 * p.nb;
     repack_q4_1_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
         d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
-  else
+  } else {
+    const long long total = (long long) p.g_total * 4 * ((p.nb + 3) / 4) * 4;
     repack_q4_0_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
-        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half);
+        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half, p.lp);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   m->weight_bytes += (long long) p.M * p.nb * (p.qtype == 3 ? 24 : 20);
@@ -743,7 +740,6 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     for (int i = 0; i < m->n_layer; i++) {
       descs[i].qkv = mat_desc(m->layers[i].qkv); descs[i].wo = mat_desc(m->layers[i].wo);
       descs[i].w13 = mat_desc(m->layers[i].w13); descs[i].w2 = mat_desc(m->layers[i].w2);
-      descs[i].qkv.pad = 0; descs[i].w13.pad = 0;      // producer/chain mode is for the small matrices (wo, w2) only
       descs[i].attn_norm = m->layers[i].attn_norm; descs[i].ffn_norm = m->layers[i].ffn_norm;
       descs[i].k_layer = m->d_k + (size_t) i * n_ctx * E; descs[i].v_layer = m->d_v + (size_t) i * n_ctx * E;
     }
@@ -753,24 +749,17 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     CUDA_TRY(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned int)));
     // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
-    const int nb_max = std::max(E, F) / 32;
+    const int nb_max = ((std::max(E, F) / 32) + 3) & ~3;     // whole quads
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
-    for (auto &L : m->layers) {
-      if (L.wo.split) m->mega_split_rows = std::max(m->mega_split_rows, L.wo.rmax);
-      if (L.w2.split) m->mega_split_rows = std::max(m->mega_split_rows, L.w2.rmax);
-      L.qkv.split = 0; L.w13.split = 0;
-    }
-    m->out.split = 0;
-    const size_t fixed = (size_t) 2 * SPLIT_SB * m->mega_split_rows * 36 +
-                         (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
+    const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
                          MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
-    bool fits = rmax_all * 20 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
+    bool fits = rmax_all * 80 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
     auto rows_fit = [&](const GemvPlan &p) { return p.rmax * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
     fits = fits && rows_fit(m->out);
     for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);

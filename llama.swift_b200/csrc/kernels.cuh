@@ -47,12 +47,131 @@ __host__ __device__ __forceinline__ int cta_of_granule(int g_total, int n_cta, i
   return rem + (g - rem * (q + 1)) / q;
 }
 
-// Tile-major weight stream.  CTA c owns rows [row0, row0+R) and its bytes are contiguous at row0*nb*20.
-// Inside, chunk k (cb blocks, the last one shorter) is [cbk][R][16 B nibbles] then [cbk][R] f32 scales, so one
-// pipeline stage is ONE cp.async.bulk.  The 16 nibble bytes of a block are permuted so that 32-bit word p holds
-// AVX2 accumulator lane 2p in its low nibbles and lane 2p+1 in its high nibbles (lane l = elements 2l,2l+1,16+2l,17+2l
-// of the block, ggml.c:1443-1452): `w & 0x0f0f0f0f` / `w & 0xf0f0f0f0` are then directly dp4a operands.
+// Tile-major weight stream ("quad-major").  CTA c owns rows [row0, row0+R) and its bytes are contiguous at
+// row0 * nbq * 80, nbq = ceil(nb / 4) quads of 4 blocks per row (same 20 bytes per 32 weights as ggml, ggml.c:408; a
+// partial last quad is padded with zero-scale blocks, which are exact no-ops).  Chunk k (cq quads, the last one shorter)
+// is one contiguous piece, so one pipeline stage is ONE cp.async.bulk.  Inside a quad:
+//
+//     [lane-pair slot j < LP][row r < R][thread-of-row t < 4/LP][block b < 4]  32-bit nibble words   (R * 64 bytes)
+//     [row r][block b]                                                         f32 block scales     (R * 16 bytes)
+//
+// where LP = lane pairs per thread of the matrix's plan and word p = t*LP + j of a block holds AVX2 accumulator lane 2p
+// in its low nibbles and lane 2p+1 in its high nibbles (lane l = elements 2l, 2l+1, 16+2l, 17+2l of the block,
+// ggml.c:1443-1452), so `w & 0x0f0f0f0f` / `w & 0xf0f0f0f0` are directly dp4a operands.  The point of this order:
+// the thread that owns (row r, lane pairs t*LP..t*LP+LP-1) gets its words of FOUR blocks with one 16-byte shared-memory
+// load per j and the four scales with another -- consecutive threads read consecutive 16 bytes (conflict-free), all
+// block offsets are immediates, and the only per-quad address arithmetic is one pointer increment.  The row loop is
+// issue-bound on the FMA pipe (IDP.4A, FFMA2, IMAD share it), so instructions per (row, block) are what matters.
 __device__ __forceinline__ int lane_elem(int lane, int k) { return (k < 2 ? 0 : 16) + 2 * lane + (k & 1); }
+
+#ifndef B200_PIPE
+#define B200_PIPE 1         // LP == 1: two quads in registers, the loads of quad q+1 are issued under the math of quad q
+#endif
+
+template <int LP>
+struct QuadRegs {
+  uint4 w[LP];     // nibble words of 4 blocks for each of this thread's lane pairs
+  float4 sc;       // weight scales of the 4 blocks (row r)
+  float4 dx;       // activation scales of the 4 blocks
+};
+
+template <int LP>
+__device__ __forceinline__ void quad_load(QuadRegs<LP> &q, const uint8_t *pw, const uint8_t *ps, const float *pd, int jstride) {
+#pragma unroll
+  for (int j = 0; j < LP; j++) q.w[j] = *reinterpret_cast<const uint4 *>(pw + j * jstride);
+  q.sc = *reinterpret_cast<const float4 *>(ps);
+  q.dx = *reinterpret_cast<const float4 *>(pd);
+}
+
+// one block of one quad: acc[j] = fma(d_w * d_x, (float) isum_j, acc[j]) for this thread's LP lane pairs
+template <int LP>
+__device__ __forceinline__ void block_math(const uint32_t (&w)[LP], float sc, float dx, const uint4 (&x)[LP], u64 (&acc)[LP],
+                                           const u64 cvt_mul, const u64 cvt_sub) {
+  const float sdx = __fmul_rn(sc, dx);                                           // _mm256_mul_ps(d0, d1), ggml.c:1431
+#pragma unroll
+  for (int j = 0; j < LP; j++) {
+    const int ia = dp4a_us(w[j] & 0x0F0F0F0Fu, (int) x[j].x, (int) x[j].z);      // float bits of 12582912 + isum(lane 2p)
+    const int ib = dp4a_us(w[j] & 0xF0F0F0F0u, (int) x[j].y, (int) x[j].w);      // float bits of 12582912 + 16*isum(lane 2p+1)
+    const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                      // exact (float)isum for both lanes
+    acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                                // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+  }
+}
+
+template <int LP>
+__device__ __forceinline__ void quad_math(const QuadRegs<LP> &q, const uint4 *px, u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
+  const float sc[4] = {q.sc.x, q.sc.y, q.sc.z, q.sc.w};
+  const float dx[4] = {q.dx.x, q.dx.y, q.dx.z, q.dx.w};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    uint32_t w[LP];
+    uint4 x[LP];
+#pragma unroll
+    for (int j = 0; j < LP; j++) {
+      w[j] = b == 0 ? q.w[j].x : b == 1 ? q.w[j].y : b == 2 ? q.w[j].z : q.w[j].w;
+      x[j] = px[b * 4 + j];
+    }
+    block_math<LP>(w, sc[b], dx[b], x, acc, cvt_mul, cvt_sub);
+  }
+}
+
+// All quads of one chunk (stage `st`, cqk quads) for the thread that owns (row r, lane pairs t*LP .. t*LP+LP-1).
+// px = quantized activation of the chunk's first block + t*LP ([block][4] uint4), pd = its activation scales.
+template <int LP>
+__device__ __forceinline__ void gemv_chunk(const uint8_t *st, int cqk, int R, int r, int t, const uint4 *px, const float *pd,
+                                           u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
+  constexpr int UPR = 4 / LP;
+  const int jstride = R * UPR * 16;             // bytes between lane-pair slots
+  const int qstride = R * 80;                   // bytes per quad
+  const uint8_t *pw = st + (r * UPR + t) * 16;
+  const uint8_t *ps = st + R * 64 + r * 16;
+  int q = 0;
+#if B200_PIPE
+  if constexpr (LP == 1) {
+    // Two register sets: the look-ahead may read one quad past the end of the chunk -- still inside this CTA's shared
+    // memory, and the values are never used.
+    QuadRegs<1> ra, rb;
+    uint4 xa[4], xb[4];
+    quad_load<1>(ra, pw, ps, pd, jstride);
+#pragma unroll
+    for (int b = 0; b < 4; b++) xa[b] = px[b * 4];
+    for (; q + 2 <= cqk; q += 2) {
+      quad_load<1>(rb, pw + qstride, ps + qstride, pd + 4, jstride);
+#pragma unroll
+      for (int b = 0; b < 4; b++) xb[b] = px[16 + b * 4];
+      {
+        const float sc[4] = {ra.sc.x, ra.sc.y, ra.sc.z, ra.sc.w}, dx[4] = {ra.dx.x, ra.dx.y, ra.dx.z, ra.dx.w};
+        const uint32_t wv[4] = {ra.w[0].x, ra.w[0].y, ra.w[0].z, ra.w[0].w};
+#pragma unroll
+        for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xa[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
+      }
+      quad_load<1>(ra, pw + 2 * qstride, ps + 2 * qstride, pd + 8, jstride);
+#pragma unroll
+      for (int b = 0; b < 4; b++) xa[b] = px[32 + b * 4];
+      {
+        const float sc[4] = {rb.sc.x, rb.sc.y, rb.sc.z, rb.sc.w}, dx[4] = {rb.dx.x, rb.dx.y, rb.dx.z, rb.dx.w};
+        const uint32_t wv[4] = {rb.w[0].x, rb.w[0].y, rb.w[0].z, rb.w[0].w};
+#pragma unroll
+        for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xb[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
+      }
+      pw += 2 * qstride; ps += 2 * qstride; px += 32; pd += 8;
+    }
+    if (q < cqk) {
+      const float sc[4] = {ra.sc.x, ra.sc.y, ra.sc.z, ra.sc.w}, dx[4] = {ra.dx.x, ra.dx.y, ra.dx.z, ra.dx.w};
+      const uint32_t wv[4] = {ra.w[0].x, ra.w[0].y, ra.w[0].z, ra.w[0].w};
+#pragma unroll
+      for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xa[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
+    }
+    return;
+  }
+#endif
+#pragma unroll 2
+  for (; q < cqk; q++) {
+    QuadRegs<LP> rq;
+    quad_load<LP>(rq, pw, ps, pd, jstride);
+    quad_math<LP>(rq, px, acc, cvt_mul, cvt_sub);
+    pw += qstride; ps += qstride; px += 16; pd += 4;
+  }
+}
 
 enum GemvPrologue { PRO_PLAIN = 0, PRO_NORM = 1 };
 enum GemvEpilogue { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU_MUL = 3 };
@@ -62,7 +181,7 @@ struct GemvArgs {
   int M;                  // valid (unpadded) fused rows
   int g_total;            // padded rows / 4
   int nb;                 // blocks per row = K/32
-  int cb;                 // blocks per chunk
+  int cb;                 // blocks per chunk (a multiple of 4: whole quads)
   int n_stages;
   int stage_bytes;
   int rmax;
@@ -152,14 +271,16 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   const int nb = a.nb;
   const RowPart rp = row_part(a.g_total, gridDim.x, blockIdx.x);
   const int R = rp.R;
-  const int nchunks = (nb + a.cb - 1) / a.cb;
+  const int nbq = (nb + 3) >> 2, cq = a.cb >> 2;       // quads per row / per chunk
+  const int nbp = nbq * 4;                              // blocks incl. the zero padding of a partial last quad
+  const int nchunks = (nbq + cq - 1) / cq;
   const int S = a.n_stages;
 
   // shared memory carve-up
   uint8_t *stages = smem;
-  uint4 *xq = reinterpret_cast<uint4 *>(smem + (size_t) S * a.stage_bytes);   // [nb][4] {xsA, xsB, cA, cB}
-  float *dxs = reinterpret_cast<float *>(xq + (size_t) nb * 4);               // [nb]
-  float *rowres = dxs + ((nb + 3) & ~3);                                        // [rmax]
+  uint4 *xq = reinterpret_cast<uint4 *>(smem + (size_t) S * a.stage_bytes);   // [nbp][4] {xsA, xsB, cA, cB}
+  float *dxs = reinterpret_cast<float *>(xq + (size_t) nbp * 4);              // [nbp]
+  float *rowres = dxs + nbp;                                                    // [rmax]
   double *red = reinterpret_cast<double *>(rowres + ((a.rmax + 3) & ~3));       // [32]
   uint64_t *full = reinterpret_cast<uint64_t *>(red + 32);                      // [S]
   uint64_t *empty = full + S;                                                   // [S]
@@ -173,14 +294,14 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   if (tid >= nt) {
     // ===== TMA producer: stream this CTA's contiguous weight bytes; does not depend on the upstream kernel =====
     if (tid == nt) {
-      const uint8_t *wbase = a.w + (size_t) rp.row0 * nb * 20;
+      const uint8_t *wbase = a.w + (size_t) rp.row0 * nbq * 80;
       for (int k = 0; k < nchunks; k++) {
         const int s = k % S;
         if (k >= S) mbar_wait(&empty[s], ((k / S) - 1) & 1);
-        const int cbk = min(a.cb, nb - k * a.cb);
-        const uint32_t bytes = (uint32_t) cbk * R * 20;
+        const int cqk = min(cq, nbq - k * cq);
+        const uint32_t bytes = (uint32_t) cqk * R * 80;
         mbar_arrive_expect_tx(&full[s], bytes);
-        tma_bulk_g2s(stages + (size_t) s * a.stage_bytes, wbase + (size_t) k * a.cb * R * 20, bytes, &full[s]);
+        tma_bulk_g2s(stages + (size_t) s * a.stage_bytes, wbase + (size_t) k * cq * R * 80, bytes, &full[s]);
       }
     }
     return;
@@ -255,6 +376,11 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
     for (int p = 0; p < 4; p++) xq[b * 4 + p] = make_uint4(xs[2 * p], xs[2 * p + 1], (uint32_t) cc[2 * p], (uint32_t) cc[2 * p + 1]);
     dxs[b] = d;
   }
+  for (int b = nb + tid; b < nbp; b += nt) {        // padding blocks of a partial last quad: scale 0 on both sides = exact no-op
+#pragma unroll
+    for (int p = 0; p < 4; p++) xq[b * 4 + p] = make_uint4(0u, 0u, 0u, 0u);
+    dxs[b] = 0.0f;
+  }
   named_bar_sync(1, nt);
 
   // ---- main loop: 8 exact AVX2 lanes per row, LP lane-pairs per thread ----
@@ -271,34 +397,9 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   for (int k = 0; k < nchunks; k++) {
     const int s = k % S;
     mbar_wait(&full[s], (k / S) & 1);
-    const int cbk = min(a.cb, nb - k * a.cb);
-    const uint8_t *st = stages + (size_t) s * a.stage_bytes;
-    const uint32_t *nib = reinterpret_cast<const uint32_t *>(st) + (size_t) r * 4 + pg * LP;
-    const float *sc = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16) + r;
-    const uint4 *xqk = xq + (size_t) k * a.cb * 4 + pg * LP;
-    const float *dxk = dxs + k * a.cb;
-#pragma unroll 4
-    for (int bl = 0; bl < cbk; bl++) {
-      uint32_t wv[LP];
-      if constexpr (LP == 4) {
-        const uint4 t = *reinterpret_cast<const uint4 *>(nib + (size_t) bl * R * 4);
-        wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
-      } else if constexpr (LP == 2) {
-        const uint2 t = *reinterpret_cast<const uint2 *>(nib + (size_t) bl * R * 4);
-        wv[0] = t.x; wv[1] = t.y;
-      } else {
-        wv[0] = nib[(size_t) bl * R * 4];
-      }
-      const float sdx = __fmul_rn(sc[bl * R], dxk[bl]);                          // _mm256_mul_ps(d0, d1), ggml.c:1431
-#pragma unroll
-      for (int j = 0; j < LP; j++) {
-        const uint4 xv = xqk[bl * 4 + j];
-        const int ia = dp4a_us(wv[j] & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);    // float bits of 12582912 + isum(lane 2p)
-        const int ib = dp4a_us(wv[j] & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);    // float bits of 12582912 + 16*isum(lane 2p+1)
-        const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                   // exact (float)isum for both lanes
-        acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                             // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
-      }
-    }
+    const int cqk = min(cq, nbq - k * cq);
+    gemv_chunk<LP>(stages + (size_t) s * a.stage_bytes, cqk, R, r, pg, xq + (size_t) k * a.cb * 4 + pg * LP, dxs + k * a.cb,
+                   acc, cvt_mul, cvt_sub);
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
   }
@@ -495,44 +596,52 @@ __global__ void __launch_bounds__(1024, 1) argmax_advance_kernel(const float *lo
   }
 }
 
-// ---- load-time repack: ggml rows of 20-byte blocks -> tile-major stream (see the layout comment above) --------------
+// ---- load-time repack: ggml rows of 20-byte blocks -> quad-major stream (see the layout comment above) --------------
 // src = concatenation of the fused matrices' raw rows.  interleave_half > 0: fused row 2i <- src row i,
-// 2i+1 <- src row interleave_half + i (w1/w3).  Rows >= M are zero padding.
+// 2i+1 <- src row interleave_half + i (w1/w3).  Rows >= M and blocks >= nb are zero padding (scale 0).
 __global__ void repack_q4_0_kernel(const uint8_t *src, uint8_t *dst, int M, int g_total, int nb, int cb, int n_cta,
-                                   int interleave_half) {
+                                   int interleave_half, int lp) {
+  const int nbq = (nb + 3) >> 2, cq = cb >> 2;
   const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long) g_total * 4 * nb;
+  const long long total = (long long) g_total * 4 * nbq * 4;
   if (idx >= total) return;
-  const int gr = (int) (idx / nb), b = (int) (idx % nb);
+  const int gr = (int) (idx / (nbq * 4)), b = (int) (idx % (nbq * 4));
   const int c = cta_of_granule(g_total, n_cta, gr / 4);
   const RowPart rp = row_part(g_total, n_cta, c);
   const int r = gr - rp.row0, R = rp.R;
-  const int k = b / cb, bl = b % cb;
-  const int cbk = min(cb, nb - k * cb);
-  uint8_t *chunk = dst + (size_t) rp.row0 * nb * 20 + (size_t) k * cb * R * 20;
-  uint4 *dn = reinterpret_cast<uint4 *>(chunk) + (size_t) bl * R + r;
-  float *ds = reinterpret_cast<float *>(chunk + (size_t) cbk * R * 16) + (size_t) bl * R + r;
-  if (gr >= M) { *dn = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u); *ds = 0.0f; return; }
-  const int sr = interleave_half > 0 ? ((gr & 1) ? interleave_half + gr / 2 : gr / 2) : gr;
-  const uint32_t *sp = reinterpret_cast<const uint32_t *>(src + ((size_t) sr * nb + b) * 20);
-  const float d = __uint_as_float(sp[0]);
-  uint32_t by[4] = {sp[1], sp[2], sp[3], sp[4]};
-  uint32_t wout[4];
+  const int qd = b >> 2, bq = b & 3;
+  const int k = qd / cq, ql = qd % cq;
+  uint8_t *quad = dst + (size_t) rp.row0 * nbq * 80 + (size_t) k * cq * R * 80 + (size_t) ql * R * 80;
+  uint32_t *dn = reinterpret_cast<uint32_t *>(quad);
+  float *ds = reinterpret_cast<float *>(quad + (size_t) R * 64) + r * 4 + bq;
+  const int upr = 4 / lp;
+  uint32_t wout[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u};
+  float d = 0.0f;
+  if (gr < M && b < nb) {
+    const int sr = interleave_half > 0 ? ((gr & 1) ? interleave_half + gr / 2 : gr / 2) : gr;
+    const uint32_t *sp = reinterpret_cast<const uint32_t *>(src + ((size_t) sr * nb + b) * 20);
+    d = __uint_as_float(sp[0]);
+    const uint32_t by[4] = {sp[1], sp[2], sp[3], sp[4]};
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      uint32_t wv = 0;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const int ea = lane_elem(2 * p, kk), eb = lane_elem(2 * p + 1, kk);
+        const uint32_t ba = (by[(ea / 2) / 4] >> (8 * ((ea / 2) % 4))) & 0xff;
+        const uint32_t bb = (by[(eb / 2) / 4] >> (8 * ((eb / 2) % 4))) & 0xff;
+        const uint32_t na = (ea & 1) ? (ba >> 4) : (ba & 0xf);
+        const uint32_t nbv = (eb & 1) ? (bb >> 4) : (bb & 0xf);
+        wv |= (na | (nbv << 4)) << (8 * kk);
+      }
+      wout[p] = wv;
+    }
+  }
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    uint32_t wv = 0;
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) {
-      const int ea = lane_elem(2 * p, kk), eb = lane_elem(2 * p + 1, kk);
-      const uint32_t ba = (by[(ea / 2) / 4] >> (8 * ((ea / 2) % 4))) & 0xff;
-      const uint32_t bb = (by[(eb / 2) / 4] >> (8 * ((eb / 2) % 4))) & 0xff;
-      const uint32_t na = (ea & 1) ? (ba >> 4) : (ba & 0xf);
-      const uint32_t nbv = (eb & 1) ? (bb >> 4) : (bb & 0xf);
-      wv |= (na | (nbv << 4)) << (8 * kk);
-    }
-    wout[p] = wv;
+    const int t = p / lp, j = p % lp;                       // word p belongs to thread t of the row, lane-pair slot j
+    dn[(((size_t) j * R + r) * upr + t) * 4 + bq] = wout[p];
   }
-  *dn = make_uint4(wout[0], wout[1], wout[2], wout[3]);
   *ds = d;
 }
 

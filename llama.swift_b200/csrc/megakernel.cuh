@@ -29,7 +29,7 @@ struct MatDesc {
   int nb;             // blocks per row
   int cb;             // blocks per chunk
   int lp;             // lane-pairs per thread (1, 2 or 4)
-  int pad;            // != 0: run this matrix in producer/chain mode (gemv_rows_split)
+  int pad;
 };
 
 struct LayerDesc {
@@ -71,7 +71,6 @@ struct TokenArgs {
   float kq_scale;
   int S, stage_bytes;
   int xs_floats;            // size of the f32 scratch area (attention scores): >= n_ctx
-  int split_rows;           // rows per CTA of the largest matrix run in producer/chain mode (0: mode off)
   int l2_ahead;             // chunks the L2-prefetch warp may run ahead of the loader (0 = off)
   long long *prof;          // optional [gridDim.x][prof_marks] globaltimer stamps (development profiler), else null
   int prof_marks;
@@ -81,7 +80,6 @@ constexpr int MEGA_COMPUTE_WARPS = 16;
 constexpr int MEGA_COMPUTE_THREADS = MEGA_COMPUTE_WARPS * 32;   // 512: one 8-float item per thread at n_embd 4096
 constexpr int MEGA_THREADS = MEGA_COMPUTE_THREADS + 32;          // + the TMA loader warp (96 regs/thread)
 constexpr int MEGA_MAX_ROWS = 512;     // rows per CTA upper bound (rowres[])
-constexpr int SPLIT_SB = 16;          // blocks per producer/chain hand-over in the small-matrix row loop
 constexpr int MEGA_MAX_NTH = 16;       // reference thread counts supported by the V*P partition
 constexpr int MEGA_NORM_ROUNDS = 2;    // 8-element items per thread held in registers by the LayerNorm prologue (K <= 7168)
 
@@ -169,10 +167,7 @@ struct MegaSmem {
   float *redf;      // [2][16]
   float *part;      // [MEGA_MAX_NTH][32]
   double2 *ropev;   // [head_dim/2] (cos, sin) of this token's position, fetched once at kernel start
-  float2 *splitF;   // [2][SPLIT_SB][split_rows][4]  exact (float)isum pairs, producer warps -> chain warps
-  float *splitS;    // [2][SPLIT_SB][split_rows]     d_w*d_x per (block,row)
   uint64_t *full, *empty;
-  volatile uint32_t *done;       // [MEGA_COMPUTE_WARPS] chunks of the token each compute warp has finished with
 };
 
 // Block-wide sums over the compute warps with ONE barrier: warp shuffle tree, 14 partials, then every warp folds the
@@ -275,6 +270,15 @@ __device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int 
   }
 }
 
+// blocks nb .. 4*ceil(nb/4)-1 pad a partial last quad: scale 0 on both sides makes them exact no-ops in the row loop
+__device__ __forceinline__ void zero_pad_blocks(int nb, const MegaSmem &sm, int tid) {
+  const int nbp = (nb + 3) & ~3;
+  if (tid < (nbp - nb) * 4) {
+    sm.xq[nb * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    if ((tid & 3) == 0) sm.dxs[nb + (tid >> 2)] = 0.0f;
+  }
+}
+
 // PLAIN: quantize x[K] (flagged words, polled) -> xq/dxs.
 template <int N>
 __device__ __forceinline__ void prologue_plain_batch(const uint2 *src, int items, int it0, uint32_t seq, long long limit,
@@ -300,6 +304,7 @@ __device__ __forceinline__ void prologue_plain(const uint2 *src, int nb, uint32_
     else if (n == 2) prologue_plain_batch<2>(src, items, it0, seq, limit, sm, tid);
     else prologue_plain_batch<1>(src, items, it0, seq, limit, sm, tid);
   }
+  zero_pad_blocks(nb, sm, tid);
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
@@ -356,6 +361,7 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
       quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
     }
   }
+  zero_pad_blocks(nb, sm, tid);
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
@@ -381,65 +387,9 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 }
 
 // ---- GEMV main loop over this CTA's rows of one matrix; leaves the row results in sm.rowres -------------------------
-// Both alternatives were measured on B200 (7B, 64 decode steps): ROWLOOP/DONE_FLAGS = 0/0 1664 us/token, 1/0 1685,
-// 0/1 1747, 1/1 1713 -- the plain loop and the mbarrier ring win; the others stay selectable for A/B builds.
-#ifndef B200_ROWLOOP
-#define B200_ROWLOOP 0      // 1: loads of U blocks batched ahead of their math; 0: unroll 4, ptxas schedules
-#endif
-#ifndef B200_DONE_FLAGS
-#define B200_DONE_FLAGS 0   // 1: stage release through per-warp progress words (idle warps sleep); 0: mbarrier ring
-#endif
 #ifndef B200_NO_MATH
 #define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
 #endif
-
-#ifndef B200_PIPE
-#define B200_PIPE 1         // 1: software-pipelined row loop (loads of group g+1 in flight under the math of group g)
-#endif
-
-// Operands of U consecutive blocks of one row (LP lane pairs each), held in registers.
-template <int LP, int U>
-struct BlkRegs {
-  uint32_t w[U][LP];
-  uint4 x[U][LP];
-  float sc[U], dx[U];
-};
-
-template <int LP, int U>
-__device__ __forceinline__ void blk_load(BlkRegs<LP, U> &b, const uint32_t *pw, const float *ps, const uint4 *px,
-                                         const float *pd, int wstride, int R) {
-#pragma unroll
-  for (int u = 0; u < U; u++) {
-    if constexpr (LP == 4) {
-      const uint4 t = *reinterpret_cast<const uint4 *>(pw + u * wstride);
-      b.w[u][0] = t.x; b.w[u][1] = t.y; b.w[u][2] = t.z; b.w[u][3] = t.w;
-    } else if constexpr (LP == 2) {
-      const uint2 t = *reinterpret_cast<const uint2 *>(pw + u * wstride);
-      b.w[u][0] = t.x; b.w[u][1] = t.y;
-    } else {
-      b.w[u][0] = pw[u * wstride];
-    }
-    b.sc[u] = ps[u * R];
-    b.dx[u] = pd[u];
-#pragma unroll
-    for (int j = 0; j < LP; j++) b.x[u][j] = px[u * 4 + j];
-  }
-}
-
-template <int LP, int U>
-__device__ __forceinline__ void blk_math(const BlkRegs<LP, U> &b, u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
-#pragma unroll
-  for (int u = 0; u < U; u++) {
-    const float sdx = __fmul_rn(b.sc[u], b.dx[u]);                               // _mm256_mul_ps(d0, d1), ggml.c:1431
-#pragma unroll
-    for (int j = 0; j < LP; j++) {
-      const int ia = dp4a_us(b.w[u][j] & 0x0F0F0F0Fu, (int) b.x[u][j].x, (int) b.x[u][j].z);   // float bits of 12582912 + isum(lane 2p)
-      const int ib = dp4a_us(b.w[u][j] & 0xF0F0F0F0u, (int) b.x[u][j].y, (int) b.x[u][j].w);   // float bits of 12582912 + 16*isum(lane 2p+1)
-      const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                   // exact (float)isum for both lanes
-      acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                             // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
-    }
-  }
-}
 
 // Position in the ring of stages: stage index and the parity of its mbarrier phase, advanced without div/mod.
 struct RingPos {
@@ -453,130 +403,29 @@ template <int LP>
 __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                           int S, int stage_bytes, int tid) {
   constexpr int UPR = 4 / LP;
-  const int R = rp.R, nb = md.nb, cb = md.cb;
-  const int nchunks = (nb + cb - 1) / cb;
+  const int R = rp.R, cb = md.cb;
+  const int nbq = (md.nb + 3) >> 2, cq = cb >> 2;
+  const int nchunks = (nbq + cq - 1) / cq;
   const bool active = tid < R * UPR;
   const int r = active ? tid / UPR : R - 1;
-  const int pg = tid % UPR;
+  const int t = tid % UPR;
   u64 acc[LP];
 #pragma unroll
   for (int j = 0; j < LP; j++) acc[j] = pack_f2(0.0f, 0.0f);
   const u64 cvt_mul = pack_f2(1.0f, 0.0625f);
   const u64 cvt_sub = pack_f2(-12582912.0f, -786432.0f);
   const bool warp_active = (tid & ~31) < R * UPR;     // warps with no rows skip the math but still release stages
-  const int wstride = R * 4;
 
-#if B200_DONE_FLAGS
-  if (!warp_active) {
-    // this warp owns no rows of this matrix: mark its share of the ring as consumed and go to sleep in the barrier
-    for (int k = 0; k < nchunks; k++) ring.next(S);
-    if ((tid & 31) == 0) sm.done[tid >> 5] = ring.g;
-  } else
-#endif
   for (int k = 0; k < nchunks; k++, ring.next(S)) {
     const int s = ring.s;
     mbar_wait(&sm.full[s], ring.par);
     if (warp_active && !B200_NO_MATH) {
-      const int cbk = min(cb, nb - k * cb);
-      const uint8_t *st = sm.stages + (size_t) s * stage_bytes;
-      const uint32_t *pw = reinterpret_cast<const uint32_t *>(st) + r * 4 + pg * LP;
-      const float *ps = reinterpret_cast<const float *>(st + cbk * R * 16) + r;
-      const uint4 *px = sm.xq + k * cb * 4 + pg * LP;
-      const float *pd = sm.dxs + k * cb;
-      int bl = 0;
-#if B200_PIPE
-      {
-        // Software pipeline over groups of U blocks with two register sets: the shared-memory loads of the next group
-        // are issued before the math of the current one, so the only serial dependence left per block is the
-        // reference's own accumulator FMA.  The look-ahead may read up to 2 groups past the end of the chunk: those
-        // addresses are still inside this CTA's shared memory and the values are never used.
-        constexpr int U = LP == 1 ? 4 : (LP == 2 ? 2 : 1);
-        const int ng = cbk / U;
-        BlkRegs<LP, U> ra, rb;
-        blk_load<LP, U>(ra, pw, ps, px, pd, wstride, R);
-        int g = 0;
-        for (; g + 2 <= ng; g += 2) {
-          blk_load<LP, U>(rb, pw + U * wstride, ps + U * R, px + U * 4, pd + U, wstride, R);
-          blk_math<LP, U>(ra, acc, cvt_mul, cvt_sub);
-          blk_load<LP, U>(ra, pw + 2 * U * wstride, ps + 2 * U * R, px + 2 * U * 4, pd + 2 * U, wstride, R);
-          blk_math<LP, U>(rb, acc, cvt_mul, cvt_sub);
-          pw += 2 * U * wstride; ps += 2 * U * R; px += 2 * U * 4; pd += 2 * U;
-        }
-        if (g < ng) {
-          blk_math<LP, U>(ra, acc, cvt_mul, cvt_sub);
-          pw += U * wstride; ps += U * R; px += U * 4; pd += U;
-          g++;
-        }
-        bl = g * U;
-      }
-#endif
-#if B200_ROWLOOP
-      constexpr int U = LP == 1 ? 8 : (LP == 2 ? 4 : 2);
-      for (; bl + U <= cbk; bl += U) {
-        uint32_t wv[U][LP];
-        uint4 xv[U][LP];
-        float scv[U], dxv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          if constexpr (LP == 4) {
-            const uint4 t = *reinterpret_cast<const uint4 *>(pw + u * wstride);
-            wv[u][0] = t.x; wv[u][1] = t.y; wv[u][2] = t.z; wv[u][3] = t.w;
-          } else if constexpr (LP == 2) {
-            const uint2 t = *reinterpret_cast<const uint2 *>(pw + u * wstride);
-            wv[u][0] = t.x; wv[u][1] = t.y;
-          } else {
-            wv[u][0] = pw[u * wstride];
-          }
-          scv[u] = ps[u * R];
-          dxv[u] = pd[u];
-#pragma unroll
-          for (int j = 0; j < LP; j++) xv[u][j] = px[u * 4 + j];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const float sdx = __fmul_rn(scv[u], dxv[u]);                           // _mm256_mul_ps(d0, d1), ggml.c:1431
-#pragma unroll
-          for (int j = 0; j < LP; j++) {
-            const int ia = dp4a_us(wv[u][j] & 0x0F0F0F0Fu, (int) xv[u][j].x, (int) xv[u][j].z);   // float bits of 12582912 + isum(lane 2p)
-            const int ib = dp4a_us(wv[u][j] & 0xF0F0F0F0u, (int) xv[u][j].y, (int) xv[u][j].w);   // float bits of 12582912 + 16*isum(lane 2p+1)
-            const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);               // exact (float)isum for both lanes
-            acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                         // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
-          }
-        }
-        pw += U * wstride; ps += U * R; px += U * 4; pd += U;
-      }
-#else
-#pragma unroll 4
-#endif
-      for (; bl < cbk; bl++) {
-        uint32_t wv[LP];
-        if constexpr (LP == 4) {
-          const uint4 t = *reinterpret_cast<const uint4 *>(pw);
-          wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
-        } else if constexpr (LP == 2) {
-          const uint2 t = *reinterpret_cast<const uint2 *>(pw);
-          wv[0] = t.x; wv[1] = t.y;
-        } else {
-          wv[0] = pw[0];
-        }
-        const float sdx = __fmul_rn(ps[0], pd[0]);
-#pragma unroll
-        for (int j = 0; j < LP; j++) {
-          const uint4 xv = px[j];
-          const int ia = dp4a_us(wv[j] & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
-          const int ib = dp4a_us(wv[j] & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
-          const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
-          acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);
-        }
-        pw += wstride; ps += R; px += 4; pd += 1;
-      }
+      const int cqk = min(cq, nbq - k * cq);
+      gemv_chunk<LP>(sm.stages + (size_t) s * stage_bytes, cqk, R, r, t, sm.xq + k * cb * 4 + t * LP, sm.dxs + k * cb,
+                     acc, cvt_mul, cvt_sub);
     }
     __syncwarp();
-#if B200_DONE_FLAGS
-    if ((tid & 31) == 0) sm.done[tid >> 5] = ring.g + 1;      // chunk ring.g of the token is consumed by this warp
-#else
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
-#endif
   }
 
   // horizontal sum exactly as ggml.c:1461-1466: (acc[k]+acc[k+4]) k<4, then (r0+r2)+(r1+r3)
@@ -600,108 +449,12 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
     const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
     res = __fadd_rn(s0, s1);
   }
-  if (active && pg == 0) sm.rowres[r] = res;
-  named_bar_sync(1, MEGA_COMPUTE_THREADS);
-}
-
-// ---- small matrices (R*4 <= 128 threads: wo, w2): producer/chain split -------------------------------------------------
-// With 28 rows per CTA only 112 threads own an accumulator chain, and the chain itself is just one FMA per block
-// (acc = fma(d_w*d_x, (float)isum, acc), strictly sequential in the reference).  Everything in front of that FMA --
-// nibble unpack, dp4a, exact int->float, the scale product -- is independent per (row, block, lane pair), so the 12
-// warps that own no chain compute it for SPLIT_SB blocks at a time into a double-buffered staging area and the 4
-// chain warps only do LDS + FFMA2.  Same operations, same order per lane: bit-identical to the one-thread-per-chain loop.
-__device__ __forceinline__ void gemv_rows_split(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
-                                                int S, int stage_bytes, int split_rows, int tid) {
-  constexpr int NCHAIN = 128;                                    // chain threads (warps 0-3): tid = 4*row + pair
-  constexpr int NPROD = MEGA_COMPUTE_THREADS - NCHAIN;           // producer threads (warps 4-15)
-  constexpr int MAXI = 6;                                        // producer items per hand-over, SPLIT_SB*32*4 / NPROD rounded up
-  const int R = rp.R, nb = md.nb, cb = md.cb;
-  const int R4 = R * 4;
-  const int subs_per_chunk = cb / SPLIT_SB;                      // host guarantees cb % SPLIT_SB == 0 and nb % SPLIT_SB == 0
-  const int nsub = nb / SPLIT_SB;
-  const bool is_chain = tid < NCHAIN;
-  const bool chain_active = tid < R4;
-  const int cr = chain_active ? tid >> 2 : R - 1, cp = tid & 3;
-  // producer: the items of one hand-over are (bl, row, pair) flattened as i = bl*R4 + 4*row + pair
-  int it_bl[MAXI], it_rp[MAXI];
-  const int n_items = SPLIT_SB * R4;
-#pragma unroll
-  for (int m = 0; m < MAXI; m++) {
-    const int i = (tid - NCHAIN) + m * NPROD;
-    it_bl[m] = (!is_chain && i < n_items) ? i / R4 : -1;
-    it_rp[m] = (!is_chain && i < n_items) ? i % R4 : 0;
-  }
-  u64 acc = pack_f2(0.0f, 0.0f);
-  const u64 cvt_mul = pack_f2(1.0f, 0.0625f);
-  const u64 cvt_sub = pack_f2(-12582912.0f, -786432.0f);
-  const int fstride = split_rows * 4;                             // float2 per block in the staging area
-
-  int cur_s = 0;
-  const uint8_t *st = nullptr;
-  int cbk = 0;
-  for (int j = 0; j <= nsub; j++) {
-    if (j < nsub && j % subs_per_chunk == 0) {                    // first hand-over of a ring chunk: wait for its bytes
-      cur_s = ring.s;
-      mbar_wait(&sm.full[cur_s], ring.par);
-      st = sm.stages + (size_t) cur_s * stage_bytes;
-      cbk = min(cb, nb - (j / subs_per_chunk) * cb);
-    }
-    if (!is_chain) {
-      if (j < nsub) {
-        const int bl0 = (j % subs_per_chunk) * SPLIT_SB;          // first block of this hand-over inside the chunk
-        float2 *F = sm.splitF + (size_t) (j & 1) * SPLIT_SB * fstride;
-        float *Sx = sm.splitS + (size_t) (j & 1) * SPLIT_SB * split_rows;
-        const uint32_t *nib = reinterpret_cast<const uint32_t *>(st);
-        const float *sc = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16);
-#pragma unroll
-        for (int m = 0; m < MAXI; m++) {
-          if (it_bl[m] >= 0) {
-            const int bl = bl0 + it_bl[m], r = it_rp[m] >> 2, pr = it_rp[m] & 3;
-            const int b = j * SPLIT_SB + it_bl[m];
-            const uint32_t wv = nib[(bl * R + r) * 4 + pr];
-            const uint4 xv = sm.xq[b * 4 + pr];
-            const int ia = dp4a_us(wv & 0x0F0F0F0Fu, (int) xv.x, (int) xv.z);
-            const int ib = dp4a_us(wv & 0xF0F0F0F0u, (int) xv.y, (int) xv.w);
-            const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);
-            float f0, f1;
-            unpack_f2(f, f0, f1);
-            F[it_bl[m] * fstride + it_rp[m]] = make_float2(f0, f1);
-            if (pr == 0) Sx[it_bl[m] * split_rows + r] = __fmul_rn(sc[bl * R + r], sm.dxs[b]);   // _mm256_mul_ps(d0, d1)
-          }
-        }
-      }
-    } else if (j >= 1) {
-      const float2 *F = sm.splitF + (size_t) ((j - 1) & 1) * SPLIT_SB * fstride + cr * 4 + cp;
-      const float *Sx = sm.splitS + (size_t) ((j - 1) & 1) * SPLIT_SB * split_rows + cr;
-      float2 fv[SPLIT_SB];
-      float sv[SPLIT_SB];
-#pragma unroll
-      for (int u = 0; u < SPLIT_SB; u++) { fv[u] = F[u * fstride]; sv[u] = Sx[u * split_rows]; }
-#pragma unroll
-      for (int u = 0; u < SPLIT_SB; u++) acc = ffma2(pack_f2(sv[u], sv[u]), pack_f2(fv[u].x, fv[u].y), acc);   // ggml.c:1457
-    }
-    named_bar_sync(1, MEGA_COMPUTE_THREADS);
-    if (j < nsub && (j % subs_per_chunk == subs_per_chunk - 1 || j == nsub - 1)) {   // chunk fully read by the producers
-      if ((tid & 31) == 0) mbar_arrive(&sm.empty[cur_s]);
-      ring.next(S);
-    }
-  }
-  if (is_chain) {   // horizontal sum exactly as ggml.c:1461-1466 (4 threads of a row hold lanes 2p, 2p+1)
-    float l0, l1;
-    unpack_f2(acc, l0, l1);
-    const float t0 = __fadd_rn(l0, __shfl_xor_sync(0xffffffffu, l0, 2));
-    const float t1 = __fadd_rn(l1, __shfl_xor_sync(0xffffffffu, l1, 2));
-    const float s0 = __fadd_rn(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
-    const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
-    if (chain_active && cp == 0) sm.rowres[cr] = __fadd_rn(s0, s1);
-  }
+  if (active && t == 0) sm.rowres[r] = res;
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
 __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
-                                              int S, int stage_bytes, int split_rows, int tid) {
-  if (rp.R == 0) { named_bar_sync(1, MEGA_COMPUTE_THREADS); return; }
-  if (md.pad != 0) { gemv_rows_split(md, rp, sm, ring, S, stage_bytes, split_rows, tid); return; }   // pad = producer/chain mode
+                                              int S, int stage_bytes, int tid) {
   switch (md.lp) {
     case 1: gemv_rows<1>(md, rp, sm, ring, S, stage_bytes, tid); break;
     case 2: gemv_rows<2>(md, rp, sm, ring, S, stage_bytes, tid); break;
@@ -823,22 +576,19 @@ extern __shared__ __align__(128) uint8_t smem_mega[];
 
 __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   const int S = a.S;
-  const int nb_max = max(a.n_embd, a.n_ff) / 32;
+  const int nb_max = ((max(a.n_embd, a.n_ff) / 32) + 3) & ~3;   // whole quads
   MegaSmem sm;
   sm.stages = smem_mega;
   sm.xq = reinterpret_cast<uint4 *>(smem_mega + (size_t) S * a.stage_bytes);
   sm.dxs = reinterpret_cast<float *>(sm.xq + (size_t) nb_max * 4);
-  sm.xs = sm.dxs + ((nb_max + 3) & ~3);
+  sm.xs = sm.dxs + nb_max;
   sm.rowres = sm.xs + a.xs_floats;
   sm.redd = reinterpret_cast<double *>(sm.rowres + MEGA_MAX_ROWS);
   sm.redf = reinterpret_cast<float *>(sm.redd + 32);
   sm.part = sm.redf + 32;
   sm.ropev = reinterpret_cast<double2 *>(sm.part + MEGA_MAX_NTH * 32);
-  sm.splitF = reinterpret_cast<float2 *>(sm.ropev + 64);
-  sm.splitS = reinterpret_cast<float *>(sm.splitF + 2 * SPLIT_SB * a.split_rows * 4);
-  sm.full = reinterpret_cast<uint64_t *>(sm.splitS + 2 * SPLIT_SB * a.split_rows);
+  sm.full = reinterpret_cast<uint64_t *>(sm.ropev + 64);
   sm.empty = sm.full + S;
-  sm.done = reinterpret_cast<volatile uint32_t *>(sm.empty + S);
   return sm;
 }
 
@@ -854,7 +604,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], MEGA_COMPUTE_WARPS); }
-    for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) sm.done[w] = 0;
     fence_mbar_init();
   }
   __syncthreads();
@@ -868,8 +617,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const bool pf_on = a.l2_ahead > 0;
     if (lane == 0 || pf_on) {
       RingPos g = {0, 0u, 0u};
-      uint32_t done_min = 0;
-      (void) done_min;
       const int n_mats = 4 * a.n_layer + 1;
       int pm_idx = 0, pk = 0;            // prefetch cursor: matrix index in the schedule, chunk within it
       uint32_t pg = 0;                   // global index of the next chunk to prefetch
@@ -877,36 +624,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         const MatDesc &md = mi < 4 * a.n_layer ? (&a.layers[mi >> 2].qkv)[mi & 3] : a.out;
         const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
         if (rp.R == 0) continue;
-        const int nchunks = (md.nb + md.cb - 1) / md.cb;
-        const uint8_t *wbase = md.w + (size_t) rp.row0 * md.nb * 20;
+        const int nbq = (md.nb + 3) >> 2, cq = md.cb >> 2;
+        const int nchunks = (nbq + cq - 1) / cq;
+        const uint8_t *wbase = md.w + (size_t) rp.row0 * nbq * 80;
         for (int k = 0; k < nchunks; k++, g.next(S)) {
           if (lane == 0) {
             const int s = g.s;
-#if B200_DONE_FLAGS
-            if (g.g >= (uint32_t) S) {
-              const uint32_t need = g.g - (uint32_t) S + 1u;
-              if (done_min < need) {
-                const long long t0 = clock64();
-                for (;;) {
-                  uint32_t mn = 0xffffffffu;
-#pragma unroll
-                  for (int w = 0; w < MEGA_COMPUTE_WARPS; w++) mn = min(mn, sm.done[w]);
-                  done_min = mn;
-                  if (mn >= need) break;
-                  if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              }
-            }
-#else
             // g.par is the parity of the fill about to start; the slot is free once the consumers released the
             // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
             mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
-#endif
-            const int cbk = min(md.cb, md.nb - k * md.cb);
-            const uint32_t bytes = (uint32_t) cbk * rp.R * 20;
+            const int cqk = min(cq, nbq - k * cq);
+            const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
             mbar_arrive_expect_tx(&sm.full[s], bytes);
-            tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * md.cb * rp.R * 20, bytes, &sm.full[s]);
+            tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s]);
           }
           if (pf_on) {
             __syncwarp();
@@ -915,12 +645,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
             while (pm_idx < n_mats && pg < hi) {
               const MatDesc &pd = pm_idx < 4 * a.n_layer ? (&a.layers[pm_idx >> 2].qkv)[pm_idx & 3] : a.out;
               const RowPart pr = row_part(pd.g_total, gridDim.x, blockIdx.x);
-              const int pn = pr.R == 0 ? 0 : (pd.nb + pd.cb - 1) / pd.cb;
+              const int pnbq = (pd.nb + 3) >> 2, pcq = pd.cb >> 2;
+              const int pn = pr.R == 0 ? 0 : (pnbq + pcq - 1) / pcq;
               if (pk >= pn) { pm_idx++; pk = 0; continue; }
               if (pg >= lo) {
-                const int pc = min(pd.cb, pd.nb - pk * pd.cb);
-                const uint8_t *pp = pd.w + (size_t) pr.row0 * pd.nb * 20 + (size_t) pk * pd.cb * pr.R * 20;
-                const int pbytes = pc * pr.R * 20;
+                const int pc = min(pcq, pnbq - pk * pcq);
+                const uint8_t *pp = pd.w + (size_t) pr.row0 * pnbq * 80 + (size_t) pk * pcq * pr.R * 80;
+                const int pbytes = pc * pr.R * 80;
                 for (int off = lane * 128; off < pbytes; off += 32 * 128)
                   asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off));
               }
@@ -1021,7 +752,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     PROF_MARK();
 
     // ---- the mat-vec ----
-    gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, a.split_rows, tid);
+    gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, tid);
     PROF_MARK();
 
     // ---- epilogue ----

@@ -1,0 +1,23 @@
+#!/bin/bash
+# GPU session (1 x B200): parity tests + A/B of the quad-major row loop, phase profile, bench.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log
+timeout 600 python -c "import bench; bench.ensure_model(32)" > gpurun_out/model.log 2>&1
+ln -sf /tmp/b200_bench/ggml-model-q4_0.bin /tmp/probe-7b-l32.bin
+P="timeout 300 python tools/probe.py --layers 32 --steps 64"
+rm -f gpurun_out/ab.log
+for v in new nopipe v1; do
+  lib=llama.swift_b200/libb200llama.so
+  [ $v = nopipe ] && lib=llama.swift_b200/libb200llama_nopipe.so
+  [ $v = v1 ] && lib=llama.swift_b200/libb200llama_v1.so
+  echo "== $v" >> gpurun_out/ab.log
+  B200_LIB=$PWD/$lib $P 2>&1 | grep -E "decode|rror" | tail -1 >> gpurun_out/ab.log
+done
+for e in "B200_LP_SMALL=2" "B200_LP_QKV=1" "B200_LP_W13=4" "B200_LP_OUT=4" "B200_STAGE_BYTES=49152" "B200_STAGE_BYTES=24576" "B200_L2_AHEAD=64"; do
+  echo "== new $e" >> gpurun_out/ab.log
+  env $e $P 2>&1 | grep -E "decode|rror" | tail -1 >> gpurun_out/ab.log
+done
+cat gpurun_out/ab.log
+timeout 300 python tools/phase_profile.py --layers 8 --pos 64 > gpurun_out/phase.log 2>&1; tail -22 gpurun_out/phase.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json
