@@ -65,7 +65,7 @@ int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 32768) & ~127; }
+int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 49152) & ~127; }   // 48 KB measured best on B200 (4 ring stages)
 
 // Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
 GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
@@ -297,6 +297,15 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
     a.tp.ll[p] = reinterpret_cast<uint2 *>(base);
     a.tp.logits[p] = reinterpret_cast<float *>(base + m->xchg_ll_bytes);
     a.tp.done[p] = reinterpret_cast<unsigned int *>(base + m->xchg_ll_bytes + (size_t) m->n_vocab * 4);
+    a.tp.hint[p] = a.tp.done[p] + MEGA_MAX_TP;
+  }
+  {
+    // producer CTAs per layer over the whole group (every rank has the same shapes): CTAs that own rows of wo / w2
+    // (n_embd / tp rows), of w1|w3 (2 n_ff / tp fused rows), and the attention CTAs (4 per head)
+    const unsigned int ge = (unsigned int) ((m->e_loc + 3) / 4), gf = (unsigned int) ((2 * m->f_loc + 3) / 4);
+    a.tp.p_e = (unsigned int) m->tp_size * std::min<unsigned int>((unsigned int) m->n_sm, ge);
+    a.tp.p_f = (unsigned int) m->tp_size * std::min<unsigned int>((unsigned int) m->n_sm, gf);
+    a.tp.p_att = 4u * (unsigned int) m->n_head;
   }
   a.epoch = m->d_epoch;
   // a spin-wait that outlives this many clock ticks traps instead of hanging the GPU; a multi-GPU group has to
@@ -718,9 +727,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   CUDA_TRY(cudaMalloc(&m->d_att, E * 4));
   CUDA_TRY(cudaMalloc(&m->d_h, (size_t) F * 4));
   // exchange area: flagged activations inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F] (8 B per value), then the logits,
-  // then the end-of-token flags.  One allocation = one IPC handle; zero-filled, so no flag matches a live sequence number.
+  // then the end-of-token flags and the arrival-hint counters.  One allocation = one IPC handle; zero-filled, so no flag matches a live sequence number.
   m->xchg_ll_bytes = ((size_t) 6 * E + (size_t) 2 * F) * 8;
-  m->xchg_bytes = m->xchg_ll_bytes + (size_t) V * 4 + MEGA_MAX_TP * 4 + 256;
+  m->xchg_bytes = m->xchg_ll_bytes + (size_t) V * 4 + MEGA_MAX_TP * 4 + 4 * 4 + 256;
   CUDA_TRY(cudaMalloc(&m->d_xchg, m->xchg_bytes));
   CUDA_TRY(cudaMemset(m->d_xchg, 0, m->xchg_bytes));
   m->d_logits = reinterpret_cast<float *>(m->d_xchg + m->xchg_ll_bytes);

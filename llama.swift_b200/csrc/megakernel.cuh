@@ -51,6 +51,8 @@ struct TpArgs {
   uint2 *ll[MEGA_MAX_TP];             // peer p's flagged activation area (p == rank: the local one)
   float *logits[MEGA_MAX_TP];         // peer p's logits vector [n_vocab]
   unsigned int *done[MEGA_MAX_TP];    // peer p's end-of-token flags [size]
+  unsigned int *hint[MEGA_MAX_TP];    // peer p's arrival counters [4]: inpL, inpFF, att, h (monotonic, never reset)
+  unsigned int p_e, p_f, p_att;       // producer CTAs per layer over the whole group: wo/w2 rows, w1|w3 rows, attention
 };
 
 struct TokenArgs {
@@ -136,6 +138,28 @@ struct TokenArgs;
 // store one activation value into the flagged area of every GPU of the group (the local one included)
 __device__ __forceinline__ void ll_bcast(uint2 *const (&ll)[MEGA_MAX_TP], int n_peers, uint32_t off, float v, uint32_t seq) {
   for (int p = 0; p < n_peers; p++) ll_store(ll[p] + off, v, seq);
+}
+
+// Arrival hints.  Correctness never depends on them (every flagged word is verified by its reader); they only tell a
+// consumer CTA WHEN a full read is likely to succeed, so that one thread polls one word with back-off instead of 512
+// threads hammering L2 with re-reads while the producers are still working.  Relaxed atomics, no fences.
+enum { HINT_INPL = 0, HINT_INPFF = 1, HINT_ATT = 2, HINT_H = 3 };
+__device__ __forceinline__ void hint_arrive(unsigned int *const (&hint)[MEGA_MAX_TP], int n_peers, int which) {
+  for (int p = 0; p < n_peers; p++)
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(hint[p] + which) : "memory");
+}
+// thread 0 waits until the local counter reached `expected` (wrap-safe), then the CTA's compute threads go on together
+__device__ __forceinline__ void hint_wait(const unsigned int *cnt, unsigned int expected, long long limit, int tid) {
+  if (tid == 0) {
+    if ((int) (ld_vol_u32(cnt) - expected) < 0) {
+      const long long t0 = clock64();
+      while ((int) (ld_vol_u32(cnt) - expected) < 0) {
+        __nanosleep(40);
+        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+      }
+    }
+  }
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
 // Grid barrier for the compute warps (the loader warp never joins: it only obeys the ring).
@@ -387,6 +411,12 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 }
 
 // ---- GEMV main loop over this CTA's rows of one matrix; leaves the row results in sm.rowres -------------------------
+#ifndef B200_EVICT_FIRST
+#define B200_EVICT_FIRST 1  // weight stream marked evict_first in L2 (read once per token)
+#endif
+#ifndef B200_HINTS
+#define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
+#endif
 #ifndef B200_NO_MATH
 #define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
 #endif
@@ -569,6 +599,8 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     float o = sm.part[lane];
     for (int t = 1; t < nth; t++) o = __fadd_rn(o, sm.part[t * 32 + lane]);
     ll_bcast(a.tp.ll, a.tp.size, att_off + h * HD + qr * 32 + lane, o, seq);      // KQV_merged, PO.mm:641-646 -> every GPU
+    __syncwarp();
+    if (lane == 0) hint_arrive(a.tp.hint, a.tp.size, HINT_ATT);
   }
 }
 
@@ -617,6 +649,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const bool pf_on = a.l2_ahead > 0;
     if (lane == 0 || pf_on) {
       RingPos g = {0, 0u, 0u};
+#if B200_EVICT_FIRST
+      const uint64_t l2pol = l2_policy_evict_first();
+#endif
       const int n_mats = 4 * a.n_layer + 1;
       int pm_idx = 0, pk = 0;            // prefetch cursor: matrix index in the schedule, chunk within it
       uint32_t pg = 0;                   // global index of the next chunk to prefetch
@@ -636,7 +671,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
             const int cqk = min(cq, nbq - k * cq);
             const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
             mbar_arrive_expect_tx(&sm.full[s], bytes);
+#if B200_EVICT_FIRST
+            tma_bulk_g2s_hint(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s], l2pol);
+#else
             tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s]);
+#endif
           }
           if (pf_on) {
             __syncwarp();
@@ -683,6 +722,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // parity so a fast producer of layer l+1 can never overwrite words a slow consumer of layer l still polls
   const uint32_t o_inpL = 0u, o_inpFF = 2u * E, o_att = 4u * E, o_h = 6u * E;
   uint2 *const ll_me = a.tp.ll[rank];
+  // arrival-hint counters never reset: before this launch every buffer kind saw (epoch-1)*n_layer rounds of arrivals
+  const unsigned int *const hint_me = a.tp.hint[rank];
+  const unsigned int rounds0 = (epoch - 1u) * (unsigned int) a.n_layer;
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
   unsigned int phase = 0;
@@ -715,8 +757,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
     // ---- prologue ----
     if (kind == PH_WO) {
+      if (B200_HINTS) hint_wait(hint_me + HINT_ATT, (rounds0 + il + 1u) * a.tp.p_att, limit, tid);
       prologue_plain(ll_me + o_att + par * E, E / 32, seq, limit, sm, tid);     // PO.mm:649-651
     } else if (kind == PH_W2) {
+      if (B200_HINTS) hint_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
       prologue_plain(ll_me + o_h + par * F, F / 32, seq, limit, sm, tid);       // PO.mm:682-684
     } else {
       double xd[MEGA_NORM_ROUNDS][8];
@@ -744,6 +788,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           }
         }
       } else {
+        // inpFF(l) is round rounds0+l+1 of its counter; inpL(l), l >= 1, is round rounds0+l of its own (layer 0's input
+        // is the embedding row: no arrival)
+        if (B200_HINTS) {
+          if (kind == PH_W13) hint_wait(hint_me + HINT_INPFF, (rounds0 + il + 1u) * a.tp.p_e, limit, tid);
+          else hint_wait(hint_me + HINT_INPL, (rounds0 + il) * a.tp.p_e, limit, tid);
+        }
         load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, E / 32, seq, limit, tid);
       }
       const float *nw = kind == PH_QKV ? L.attn_norm : kind == PH_W13 ? L.ffn_norm : a.final_norm;
@@ -786,6 +836,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, __fmul_rn(sv, sm.rowres[2 * i + 1]), seq);
         }
       }
+      if (B200_HINTS) {
+        named_bar_sync(1, MEGA_COMPUTE_THREADS);
+        if (tid == 0) hint_arrive(a.tp.hint, T, HINT_H);
+      }
     } else if (kind == PH_OUT) {
       // the plain logits (PO.mm:705); every GPU of the group receives the full vector
       for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
@@ -807,6 +861,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           const float r = ll_wait1(ll_me + o_res + c0 + g, seq, limit);
           ll_bcast(a.tp.ll, T, o_dst + c0 + g, __fadd_rn(sm.rowres[i], r), seq_dst);
         }
+      }
+      if (B200_HINTS) {
+        named_bar_sync(1, MEGA_COMPUTE_THREADS);
+        if (tid == 0) hint_arrive(a.tp.hint, T, kind == PH_WO ? HINT_INPFF : HINT_INPL);
       }
     }
     PROF_MARK();
