@@ -56,7 +56,7 @@ struct GemvPlan {
   int qtype = 2;            // 2 = Q4_0 (20 B / 32 weights), 3 = Q4_1 (24 B / 32 weights)
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
-  int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
+  int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rpt = 1, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
   size_t smem = 0;
 };
 
@@ -65,7 +65,7 @@ int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 49152) & ~127; }   // 48 KB measured best on B200 (4 ring stages)
+int stage_bytes_cfg() { return env_int("B200_STAGE_BYTES", 57344) & ~127; }   // 56 KB measured best on B200 (3 ring stages of 56 KB)
 
 // Partition + pipeline geometry for one fused matrix of M rows x K columns on n_sm SMs.
 GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
@@ -77,9 +77,21 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   p.g_total = Mpad / 4;
   p.n_cta = std::min(n_sm, p.g_total);
   p.rmax = 4 * ((p.g_total + p.n_cta - 1) / p.n_cta);
-  int lp = p.rmax <= 40 ? 1 : (p.rmax <= 160 ? 2 : 4);   // measured best on B200 (profiles/r1_b_*)
-  if (lp_override == 1 || lp_override == 2 || lp_override == 4) lp = lp_override;
-  while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;
+  // (lane pairs per thread, rows per thread) of the whole-token kernel's row loop.  The loop is bound by shared-memory
+  // wavefronts, so the activation operands are shared by several rows of a thread where there are rows to spare;
+  // few-row matrices keep one row and one lane pair per thread (4 warps, one per SM sub-partition).
+  // lp_override: 1, 2, 4 = lane pairs (rows per thread 1); 12, 14, 22 = (1,2), (1,4), (2,2).
+  // Measured on B200 (7B): one row per thread and as many threads as fit wins -- the row phases then run at 5-6.5 TB/s,
+  // i.e. at HBM speed; sharing activation operands between 2 or 4 rows of a thread (fewer, fatter threads) was slower.
+  int lp = p.rmax <= 128 ? 1 : 2;
+  int rpt = 1;
+  if (lp_override == 1 || lp_override == 2 || lp_override == 4) { lp = lp_override; rpt = 1; }
+  if (lp_override == 12) { lp = 1; rpt = 2; }
+  if (lp_override == 14) { lp = 1; rpt = 4; }
+  if (lp_override == 22) { lp = 2; rpt = 2; }
+  while (p.rmax * (4 / lp) > MEGA_COMPUTE_THREADS && lp < 4) lp *= 2;     // (the per-matrix kernels run one row per thread)
+  if (lp == 4) rpt = 1;
+  p.rpt = rpt;
   if (qtype == 3) {
     // Q4_1: one thread per row (the reference dot is a single sequential chain per row); at least 4 compute warps
     // for the prologue.  Stage = cb blocks x rmax rows x 24 B; smem also holds the dequantized activation (K floats).
@@ -275,7 +287,7 @@ int attn_smem_bytes(const b200_llama *m, int n_threads) {
 // One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
 MatDesc mat_desc(const GemvPlan &p) {
   MatDesc d = {};
-  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.pad = 0;
+  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.rpt = p.rpt;
   return d;
 }
 
@@ -761,7 +773,7 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     const int nb_max = ((std::max(E, F) / 32) + 3) & ~3;     // whole quads
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
-    const size_t fixed = (size_t) nb_max * 64 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
+    const size_t fixed = (size_t) (nb_max + 2) * 32 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
                          MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
@@ -769,7 +781,7 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
     bool fits = rmax_all * 80 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
-    auto rows_fit = [&](const GemvPlan &p) { return p.rmax * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
+    auto rows_fit = [&](const GemvPlan &p) { return p.rmax / p.rpt * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
     fits = fits && rows_fit(m->out);
     for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);
     if (!fits) m->mega_S = 0;   // falls back to the per-matrix kernels
@@ -1047,7 +1059,7 @@ long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes;
 int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta) {
   if (!m || !mega_usable(m, n_threads) || m->tp_size > 1) return -1;
   cudaSetDevice(m->device);
-  const int marks = 2 + 15 * m->n_layer + 4;
+  const int marks = 2 + 20 * m->n_layer + 8;
   if ((long long) marks * m->n_sm > cap) return -2;
   if (cudaMalloc(&m->d_prof, (size_t) marks * m->n_sm * 8) != cudaSuccess) return -3;
   cudaMemset(m->d_prof, 0, (size_t) marks * m->n_sm * 8);

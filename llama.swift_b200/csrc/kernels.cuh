@@ -57,119 +57,155 @@ __host__ __device__ __forceinline__ int cta_of_granule(int g_total, int n_cta, i
 //
 // where LP = lane pairs per thread of the matrix's plan and word p = t*LP + j of a block holds AVX2 accumulator lane 2p
 // in its low nibbles and lane 2p+1 in its high nibbles (lane l = elements 2l, 2l+1, 16+2l, 17+2l of the block,
-// ggml.c:1443-1452), so `w & 0x0f0f0f0f` / `w & 0xf0f0f0f0` are directly dp4a operands.  The point of this order:
-// the thread that owns (row r, lane pairs t*LP..t*LP+LP-1) gets its words of FOUR blocks with one 16-byte shared-memory
-// load per j and the four scales with another -- consecutive threads read consecutive 16 bytes (conflict-free), all
-// block offsets are immediates, and the only per-quad address arithmetic is one pointer increment.  The row loop is
-// issue-bound on the FMA pipe (IDP.4A, FFMA2, IMAD share it), so instructions per (row, block) are what matters.
+// ggml.c:1443-1452).  The thread that owns lane pairs t*LP..t*LP+LP-1 of rows g, g+G, ... (RPT rows per thread, G = R/RPT)
+// gets its words of FOUR blocks with one 16-byte shared-memory load per (row, j) and the four scales with another --
+// consecutive threads read consecutive 16 bytes (conflict-free), all block offsets are immediates.
+//
+// The row loop is bound by shared-memory wavefronts and FMA-pipe issue (IDP.4A, FFMA2, IMAD share that pipe), not by
+// HBM, so bytes and instructions per (row, block) are what matters:
+//   * the quantized activation is stored as 8 bytes per (block, lane pair): the signed bytes of lanes 2p and 2p+1,
+//     plane-major [p][block] so one 16-byte load covers two blocks, and it is loaded once per thread for all its rows;
+//   * no zero-point seeds: a nibble q is turned into the signed byte 16*(q-8) in place -- `(w & 0xf0f0f0f0) ^ 0x80808080`
+//     for the high nibbles, the same on `w << 4` for the low ones (offset-binary -> two's complement is one XOR of the
+//     top bit) -- so dp4a.s32.s32 gives 16 * isum exactly; seeded with 0x4B400000 the result IS the bit pattern of the
+//     float 12582912 + 16*isum, and one fma.rn.f32x2 by (1/16, 1/16) plus (-786432, -786432) yields exact (float) isum.
 __device__ __forceinline__ int lane_elem(int lane, int k) { return (k < 2 ? 0 : 16) + 2 * lane + (k & 1); }
 
 #ifndef B200_PIPE
-#define B200_PIPE 1         // LP == 1: two quads in registers, the loads of quad q+1 are issued under the math of quad q
+#define B200_PIPE 1         // small register footprints: two quads in registers, loads of quad q+1 issued under the math of quad q
 #endif
 
-template <int LP>
+template <int LP, int RPT>
 struct QuadRegs {
-  uint4 w[LP];     // nibble words of 4 blocks for each of this thread's lane pairs
-  float4 sc;       // weight scales of the 4 blocks (row r)
-  float4 dx;       // activation scales of the 4 blocks
+  uint4 w[RPT][LP];   // nibble words of 4 blocks, per row and lane-pair slot
+  float4 sc[RPT];     // weight scales of the 4 blocks, per row
+  float4 dx;          // activation scales of the 4 blocks
+  uint4 x[LP][2];     // activation bytes: [slot][blocks 0-1 | 2-3] = {lane 2p of b, lane 2p+1 of b, same for b+1}
 };
 
-template <int LP>
-__device__ __forceinline__ void quad_load(QuadRegs<LP> &q, const uint8_t *pw, const uint8_t *ps, const float *pd, int jstride) {
-#pragma unroll
-  for (int j = 0; j < LP; j++) q.w[j] = *reinterpret_cast<const uint4 *>(pw + j * jstride);
-  q.sc = *reinterpret_cast<const float4 *>(ps);
-  q.dx = *reinterpret_cast<const float4 *>(pd);
-}
+// per-thread addressing of one matrix phase
+struct QuadPtrs {
+  const uint8_t *pw;   // this thread's first nibble word of the quad (row g, slot 0)
+  const uint8_t *ps;   // row g's scales
+  const uint8_t *px;   // activation bytes of the quad's first block, plane t*LP
+  const float *pd;     // activation scales of the quad's first block
+  int jstride;         // bytes between lane-pair slots           = R * UPR * 16
+  int rstride;         // bytes between this thread's rows        = G * UPR * 16
+  int sstride;         // bytes between this thread's rows' scales = G * 16
+  int xstride;         // bytes between activation planes         = nbp * 8
+  int qstride;         // bytes per quad                          = R * 80
+};
 
-// one block of one quad: acc[j] = fma(d_w * d_x, (float) isum_j, acc[j]) for this thread's LP lane pairs
-template <int LP>
-__device__ __forceinline__ void block_math(const uint32_t (&w)[LP], float sc, float dx, const uint4 (&x)[LP], u64 (&acc)[LP],
-                                           const u64 cvt_mul, const u64 cvt_sub) {
-  const float sdx = __fmul_rn(sc, dx);                                           // _mm256_mul_ps(d0, d1), ggml.c:1431
+template <int LP, int RPT>
+__device__ __forceinline__ void quad_load(QuadRegs<LP, RPT> &q, const QuadPtrs &p, int qoff /* quads ahead */) {
+  const uint8_t *pw = p.pw + qoff * p.qstride, *ps = p.ps + qoff * p.qstride;
+#pragma unroll
+  for (int i = 0; i < RPT; i++) {
+#pragma unroll
+    for (int j = 0; j < LP; j++) q.w[i][j] = *reinterpret_cast<const uint4 *>(pw + j * p.jstride + i * p.rstride);
+    q.sc[i] = *reinterpret_cast<const float4 *>(ps + i * p.sstride);
+  }
+  q.dx = *reinterpret_cast<const float4 *>(p.pd + qoff * 4);
 #pragma unroll
   for (int j = 0; j < LP; j++) {
-    const int ia = dp4a_us(w[j] & 0x0F0F0F0Fu, (int) x[j].x, (int) x[j].z);      // float bits of 12582912 + isum(lane 2p)
-    const int ib = dp4a_us(w[j] & 0xF0F0F0F0u, (int) x[j].y, (int) x[j].w);      // float bits of 12582912 + 16*isum(lane 2p+1)
-    const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                      // exact (float)isum for both lanes
-    acc[j] = ffma2(pack_f2(sdx, sdx), f, acc[j]);                                // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+    q.x[j][0] = *reinterpret_cast<const uint4 *>(p.px + j * p.xstride + qoff * 32);
+    q.x[j][1] = *reinterpret_cast<const uint4 *>(p.px + j * p.xstride + qoff * 32 + 16);
   }
 }
 
-template <int LP>
-__device__ __forceinline__ void quad_math(const QuadRegs<LP> &q, const uint4 *px, u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
-  const float sc[4] = {q.sc.x, q.sc.y, q.sc.z, q.sc.w};
+// acc[i][j] = fma(d_w * d_x, (float) isum, acc[i][j]) for the 4 blocks of the quad in order (ggml.c:1431-1457)
+template <int LP, int RPT>
+__device__ __forceinline__ void quad_math(const QuadRegs<LP, RPT> &q, u64 (&acc)[RPT][LP]) {
+  const u64 cvt_mul = pack_f2(0.0625f, 0.0625f);
+  const u64 cvt_sub = pack_f2(-786432.0f, -786432.0f);
   const float dx[4] = {q.dx.x, q.dx.y, q.dx.z, q.dx.w};
 #pragma unroll
   for (int b = 0; b < 4; b++) {
-    uint32_t w[LP];
-    uint4 x[LP];
 #pragma unroll
-    for (int j = 0; j < LP; j++) {
-      w[j] = b == 0 ? q.w[j].x : b == 1 ? q.w[j].y : b == 2 ? q.w[j].z : q.w[j].w;
-      x[j] = px[b * 4 + j];
+    for (int i = 0; i < RPT; i++) {
+      const float sc = b == 0 ? q.sc[i].x : b == 1 ? q.sc[i].y : b == 2 ? q.sc[i].z : q.sc[i].w;
+      const float sdx = __fmul_rn(sc, dx[b]);                                    // _mm256_mul_ps(d0, d1), ggml.c:1431
+#pragma unroll
+      for (int j = 0; j < LP; j++) {
+        const uint32_t w = b == 0 ? q.w[i][j].x : b == 1 ? q.w[i][j].y : b == 2 ? q.w[i][j].z : q.w[i][j].w;
+        const uint4 xv = q.x[j][b >> 1];
+        const int xlo = (int) ((b & 1) ? xv.z : xv.x), xhi = (int) ((b & 1) ? xv.w : xv.y);
+        const int a_hi = (int) ((w & 0xF0F0F0F0u) ^ 0x80808080u);                // signed bytes 16*(q-8), lane 2p+1
+        const int a_lo = (int) (((w << 4) & 0xF0F0F0F0u) ^ 0x80808080u);         // signed bytes 16*(q-8), lane 2p
+        const int ia = dp4a_ss(a_lo, xlo, 0x4B400000);                           // float bits of 12582912 + 16*isum(lane 2p)
+        const int ib = dp4a_ss(a_hi, xhi, 0x4B400000);                           // float bits of 12582912 + 16*isum(lane 2p+1)
+        const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                  // exact (float)isum for both lanes
+        acc[i][j] = ffma2(pack_f2(sdx, sdx), f, acc[i][j]);                      // _mm256_fmadd_ps(scale, p, acc), ggml.c:1457
+      }
     }
-    block_math<LP>(w, sc[b], dx[b], x, acc, cvt_mul, cvt_sub);
   }
 }
 
-// All quads of one chunk (stage `st`, cqk quads) for the thread that owns (row r, lane pairs t*LP .. t*LP+LP-1).
-// px = quantized activation of the chunk's first block + t*LP ([block][4] uint4), pd = its activation scales.
-template <int LP>
-__device__ __forceinline__ void gemv_chunk(const uint8_t *st, int cqk, int R, int r, int t, const uint4 *px, const float *pd,
-                                           u64 (&acc)[LP], const u64 cvt_mul, const u64 cvt_sub) {
+// All quads of one chunk (stage `st`, cqk quads).  Thread (g, t) owns lane pairs t*LP .. t*LP+LP-1 of rows g + i*G.
+// xq8 = quantized activation planes [4][nbp (plane stride)] of 8 bytes, dxs = activation scales; b0 = first block of the chunk.
+template <int LP, int RPT>
+__device__ __forceinline__ void gemv_chunk(const uint8_t *st, int cqk, int R, int g, int t, const uint2 *xq8, const float *dxs,
+                                           int nbp, int b0, u64 (&acc)[RPT][LP]) {
   constexpr int UPR = 4 / LP;
-  const int jstride = R * UPR * 16;             // bytes between lane-pair slots
-  const int qstride = R * 80;                   // bytes per quad
-  const uint8_t *pw = st + (r * UPR + t) * 16;
-  const uint8_t *ps = st + R * 64 + r * 16;
+  const int G = R / RPT;
+  QuadPtrs p;
+  p.jstride = R * UPR * 16;
+  p.rstride = G * UPR * 16;
+  p.sstride = G * 16;
+  p.xstride = nbp * 8;
+  p.qstride = R * 80;
+  p.pw = st + (g * UPR + t) * 16;
+  p.ps = st + R * 64 + g * 16;
+  p.px = reinterpret_cast<const uint8_t *>(xq8 + (size_t) (t * LP) * nbp + b0);
+  p.pd = dxs + b0;
   int q = 0;
 #if B200_PIPE
-  if constexpr (LP == 1) {
-    // Two register sets: the look-ahead may read one quad past the end of the chunk -- still inside this CTA's shared
+  if constexpr (LP == 1 && RPT <= 2) {
+    // Two register sets; the look-ahead may read one quad past the end of the chunk -- still inside this CTA's shared
     // memory, and the values are never used.
-    QuadRegs<1> ra, rb;
-    uint4 xa[4], xb[4];
-    quad_load<1>(ra, pw, ps, pd, jstride);
-#pragma unroll
-    for (int b = 0; b < 4; b++) xa[b] = px[b * 4];
+    QuadRegs<LP, RPT> ra, rb;
+    quad_load<LP, RPT>(ra, p, 0);
     for (; q + 2 <= cqk; q += 2) {
-      quad_load<1>(rb, pw + qstride, ps + qstride, pd + 4, jstride);
-#pragma unroll
-      for (int b = 0; b < 4; b++) xb[b] = px[16 + b * 4];
-      {
-        const float sc[4] = {ra.sc.x, ra.sc.y, ra.sc.z, ra.sc.w}, dx[4] = {ra.dx.x, ra.dx.y, ra.dx.z, ra.dx.w};
-        const uint32_t wv[4] = {ra.w[0].x, ra.w[0].y, ra.w[0].z, ra.w[0].w};
-#pragma unroll
-        for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xa[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
-      }
-      quad_load<1>(ra, pw + 2 * qstride, ps + 2 * qstride, pd + 8, jstride);
-#pragma unroll
-      for (int b = 0; b < 4; b++) xa[b] = px[32 + b * 4];
-      {
-        const float sc[4] = {rb.sc.x, rb.sc.y, rb.sc.z, rb.sc.w}, dx[4] = {rb.dx.x, rb.dx.y, rb.dx.z, rb.dx.w};
-        const uint32_t wv[4] = {rb.w[0].x, rb.w[0].y, rb.w[0].z, rb.w[0].w};
-#pragma unroll
-        for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xb[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
-      }
-      pw += 2 * qstride; ps += 2 * qstride; px += 32; pd += 8;
+      quad_load<LP, RPT>(rb, p, 1);
+      quad_math<LP, RPT>(ra, acc);
+      quad_load<LP, RPT>(ra, p, 2);
+      quad_math<LP, RPT>(rb, acc);
+      p.pw += 2 * p.qstride; p.ps += 2 * p.qstride; p.px += 64; p.pd += 8;
     }
-    if (q < cqk) {
-      const float sc[4] = {ra.sc.x, ra.sc.y, ra.sc.z, ra.sc.w}, dx[4] = {ra.dx.x, ra.dx.y, ra.dx.z, ra.dx.w};
-      const uint32_t wv[4] = {ra.w[0].x, ra.w[0].y, ra.w[0].z, ra.w[0].w};
-#pragma unroll
-      for (int b = 0; b < 4; b++) { const uint32_t w1[1] = {wv[b]}; const uint4 x1[1] = {xa[b]}; block_math<1>(w1, sc[b], dx[b], x1, acc, cvt_mul, cvt_sub); }
-    }
+    if (q < cqk) quad_math<LP, RPT>(ra, acc);
     return;
   }
 #endif
-#pragma unroll 2
   for (; q < cqk; q++) {
-    QuadRegs<LP> rq;
-    quad_load<LP>(rq, pw, ps, pd, jstride);
-    quad_math<LP>(rq, px, acc, cvt_mul, cvt_sub);
-    pw += qstride; ps += qstride; px += 16; pd += 4;
+    QuadRegs<LP, RPT> rq;
+    quad_load<LP, RPT>(rq, p, 0);
+    quad_math<LP, RPT>(rq, acc);
+    p.pw += p.qstride; p.ps += p.qstride; p.px += 32; p.pd += 4;
+  }
+}
+
+// horizontal sum of one row exactly as ggml.c:1461-1466: (acc[k]+acc[k+4]) k<4, then (r0+r2)+(r1+r3); the LP lane pairs
+// of the row are in this thread, the others in the neighbouring 4/LP - 1 threads
+template <int LP>
+__device__ __forceinline__ float row_hsum(const u64 (&acc)[LP]) {
+  float lane[2 * LP];
+#pragma unroll
+  for (int j = 0; j < LP; j++) unpack_f2(acc[j], lane[2 * j], lane[2 * j + 1]);
+  if constexpr (LP == 4) {
+    const float r0 = __fadd_rn(lane[4], lane[0]), r1 = __fadd_rn(lane[5], lane[1]);
+    const float r2 = __fadd_rn(lane[6], lane[2]), r3 = __fadd_rn(lane[7], lane[3]);
+    return __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+  } else if constexpr (LP == 2) {
+    float rr[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) rr[i] = __fadd_rn(lane[i], __shfl_xor_sync(0xffffffffu, lane[i], 1));
+    return __fadd_rn(__fadd_rn(rr[0], rr[2]), __fadd_rn(rr[1], rr[3]));
+  } else {
+    const float t0 = __fadd_rn(lane[0], __shfl_xor_sync(0xffffffffu, lane[0], 2));
+    const float t1 = __fadd_rn(lane[1], __shfl_xor_sync(0xffffffffu, lane[1], 2));
+    const float s0 = __fadd_rn(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    return __fadd_rn(s0, s1);
   }
 }
 
@@ -278,8 +314,9 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
 
   // shared memory carve-up
   uint8_t *stages = smem;
-  uint4 *xq = reinterpret_cast<uint4 *>(smem + (size_t) S * a.stage_bytes);   // [nbp][4] {xsA, xsB, cA, cB}
-  float *dxs = reinterpret_cast<float *>(xq + (size_t) nbp * 4);              // [nbp]
+  const int nbx = nbp + 2;                              // plane stride, padded by 16 bytes against bank conflicts
+  uint2 *xq = reinterpret_cast<uint2 *>(smem + (size_t) S * a.stage_bytes);   // [4 planes p][nbx] {bytes of lane 2p, of lane 2p+1}
+  float *dxs = reinterpret_cast<float *>(xq + (size_t) nbx * 4);              // [nbp]
   float *rowres = dxs + nbp;                                                    // [rmax]
   double *red = reinterpret_cast<double *>(rowres + ((a.rmax + 3) & ~3));       // [32]
   uint64_t *full = reinterpret_cast<uint64_t *>(red + 32);                      // [S]
@@ -363,68 +400,40 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
 #pragma unroll
     for (int i = 0; i < 32; i++) q[i] = __float2int_rn(__fmul_rn(v[i], id));   // round-to-nearest-even, = stored nibble - 8
     uint32_t xs[8];
-    int cc[8];
 #pragma unroll
     for (int l = 0; l < 8; l++) {
       const int e0 = q[2 * l], e1 = q[2 * l + 1], e2 = q[16 + 2 * l], e3 = q[17 + 2 * l];
       xs[l] = (uint32_t) (e0 & 0xff) | ((uint32_t) (e1 & 0xff) << 8) | ((uint32_t) (e2 & 0xff) << 16) | ((uint32_t) (e3 & 0xff) << 24);
-      const int sx = e0 + e1 + e2 + e3;
-      // dp4a accumulator seed: 0x4B400000 is the bit pattern of 12582912.0f, so (seed + isum) IS the float 12582912+isum
-      cc[l] = 0x4B400000 - ((l & 1) ? 128 : 8) * sx;
     }
 #pragma unroll
-    for (int p = 0; p < 4; p++) xq[b * 4 + p] = make_uint4(xs[2 * p], xs[2 * p + 1], (uint32_t) cc[2 * p], (uint32_t) cc[2 * p + 1]);
+    for (int p = 0; p < 4; p++) xq[(size_t) p * nbx + b] = make_uint2(xs[2 * p], xs[2 * p + 1]);
     dxs[b] = d;
   }
   for (int b = nb + tid; b < nbp; b += nt) {        // padding blocks of a partial last quad: scale 0 on both sides = exact no-op
 #pragma unroll
-    for (int p = 0; p < 4; p++) xq[b * 4 + p] = make_uint4(0u, 0u, 0u, 0u);
+    for (int p = 0; p < 4; p++) xq[(size_t) p * nbx + b] = make_uint2(0u, 0u);
     dxs[b] = 0.0f;
   }
   named_bar_sync(1, nt);
 
-  // ---- main loop: 8 exact AVX2 lanes per row, LP lane-pairs per thread ----
+  // ---- main loop: 8 exact AVX2 lanes per row, LP lane-pairs per thread, one row per thread ----
   const int u = tid;
   const bool active = u < R * UPR;
   const int r = active ? u / UPR : R - 1;
   const int pg = u % UPR;
-  u64 acc[LP];
+  u64 acc[1][LP];
 #pragma unroll
-  for (int j = 0; j < LP; j++) acc[j] = pack_f2(0.0f, 0.0f);
-  const u64 cvt_mul = pack_f2(1.0f, 0.0625f);
-  const u64 cvt_sub = pack_f2(-12582912.0f, -786432.0f);
+  for (int j = 0; j < LP; j++) acc[0][j] = pack_f2(0.0f, 0.0f);
 
   for (int k = 0; k < nchunks; k++) {
     const int s = k % S;
     mbar_wait(&full[s], (k / S) & 1);
     const int cqk = min(cq, nbq - k * cq);
-    gemv_chunk<LP>(stages + (size_t) s * a.stage_bytes, cqk, R, r, pg, xq + (size_t) k * a.cb * 4 + pg * LP, dxs + k * a.cb,
-                   acc, cvt_mul, cvt_sub);
+    gemv_chunk<LP, 1>(stages + (size_t) s * a.stage_bytes, cqk, R, r, pg, xq, dxs, nbx, k * a.cb, acc);
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
   }
-
-  // ---- horizontal sum exactly as ggml.c:1461-1466: (acc[k]+acc[k+4]) k<4, then (r0+r2)+(r1+r3) ----
-  float lane[2 * LP];
-#pragma unroll
-  for (int j = 0; j < LP; j++) unpack_f2(acc[j], lane[2 * j], lane[2 * j + 1]);
-  float res;
-  if constexpr (LP == 4) {
-    const float r0 = __fadd_rn(lane[4], lane[0]), r1 = __fadd_rn(lane[5], lane[1]);
-    const float r2 = __fadd_rn(lane[6], lane[2]), r3 = __fadd_rn(lane[7], lane[3]);
-    res = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-  } else if constexpr (LP == 2) {
-    float rr[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) rr[i] = __fadd_rn(lane[i], __shfl_xor_sync(0xffffffffu, lane[i], 1));
-    res = __fadd_rn(__fadd_rn(rr[0], rr[2]), __fadd_rn(rr[1], rr[3]));
-  } else {
-    const float t0 = __fadd_rn(lane[0], __shfl_xor_sync(0xffffffffu, lane[0], 2));
-    const float t1 = __fadd_rn(lane[1], __shfl_xor_sync(0xffffffffu, lane[1], 2));
-    const float s0 = __fadd_rn(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
-    const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
-    res = __fadd_rn(s0, s1);
-  }
+  const float res = row_hsum<LP>(acc[0]);
   if (active && pg == 0) rowres[r] = res;
   named_bar_sync(1, nt);
 

@@ -20,6 +20,26 @@
 #pragma once
 #include "kernels.cuh"
 
+// ---- build switches (development A/B; the defaults are the measured-best settings) ---------------------------------
+#ifndef B200_EVICT_FIRST
+#define B200_EVICT_FIRST 1  // weight stream marked evict_first in L2 (read once per token)
+#endif
+#ifndef B200_PLAIN_LOCAL
+#define B200_PLAIN_LOCAL 1  // single GPU: att and h (the mat-vec inputs that need no LayerNorm) cross phases as plain f32 +
+#endif                      // release/acquire arrival counters; measured 1.0 / 2.3 us per layer faster than flagged words
+#ifndef B200_PLAIN_X
+#define B200_PLAIN_X 0      // single GPU: the same for the residual stream (inpL, inpFF); measured 0.5-1.0 us SLOWER
+#endif
+#ifndef B200_ROTATE
+#define B200_ROTATE 0       // (measured: 3.5 % SLOWER) every CTA starts its sweep over an activation vector at a different block (spreads the
+#endif                      // 148-fold re-read of the same lines over the L2 slices)
+#ifndef B200_HINTS
+#define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
+#endif
+#ifndef B200_NO_MATH
+#define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
+#endif
+
 namespace b200 {
 
 struct MatDesc {
@@ -29,7 +49,7 @@ struct MatDesc {
   int nb;             // blocks per row
   int cb;             // blocks per chunk
   int lp;             // lane-pairs per thread (1, 2 or 4)
-  int pad;
+  int rpt;            // rows per thread (1, 2 or 4)
 };
 
 struct LayerDesc {
@@ -162,6 +182,47 @@ __device__ __forceinline__ void hint_wait(const unsigned int *cnt, unsigned int 
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
+// item index with the CTA's rotation applied (idx >= items: a padding thread, re-reads the last item)
+__device__ __forceinline__ int rot_item(int idx, int items, int rot) {
+  if (idx >= items) return items - 1;
+  const int it = idx + rot;
+  return it >= items ? it - items : it;
+}
+
+// ---- the single-GPU variant of the exchange: plain f32 words, the arrival counter is authoritative -------------------
+// Flagged words cost 8 bytes per value on the consumer side, and every CTA reads every activation vector (an
+// all-gather through L2: 148 x 92 KB per layer at 7B).  Inside one GPU a release/acquire counter is cheap, so there the
+// values travel as plain f32 (half the L2 read traffic) and the counter that is only a hint for the flagged words
+// becomes the synchronisation: producers' stores -> bar.sync -> red.release.gpu; consumer: ld.acquire.gpu -> bar.sync.
+__device__ __forceinline__ void plain_arrive(unsigned int *cnt) { red_release_add_u32(cnt, 1u); }
+__device__ __forceinline__ void plain_wait(const unsigned int *cnt, unsigned int expected, long long limit, int tid) {
+  if (tid == 0) {
+    if ((int) (ld_acquire_u32(cnt) - expected) < 0) {
+      const long long t0 = clock64();
+      while ((int) (ld_acquire_u32(cnt) - expected) < 0) {
+        __nanosleep(20);
+        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+      }
+    }
+  }
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
+}
+template <int N>
+__device__ __forceinline__ void plain_read_rounds(const float *src, int items, int it0, int rot, float (&v)[N][8], int tid) {
+  float4 va[N], vc[N];
+#pragma unroll
+  for (int rd = 0; rd < N; rd++) {        // every round's loads are in flight before the first use: one L2 latency
+    const int it = rot_item(it0 + tid + rd * MEGA_COMPUTE_THREADS, items, rot);
+    va[rd] = __ldcg(reinterpret_cast<const float4 *>(src) + it * 2);
+    vc[rd] = __ldcg(reinterpret_cast<const float4 *>(src) + it * 2 + 1);
+  }
+#pragma unroll
+  for (int rd = 0; rd < N; rd++) {
+    v[rd][0] = va[rd].x; v[rd][1] = va[rd].y; v[rd][2] = va[rd].z; v[rd][3] = va[rd].w;
+    v[rd][4] = vc[rd].x; v[rd][5] = vc[rd].y; v[rd][6] = vc[rd].z; v[rd][7] = vc[rd].w;
+  }
+}
+
 // Grid barrier for the compute warps (the loader warp never joins: it only obeys the ring).
 // bar.sync orders every compute thread's global writes before thread 0's gpu-scope release; the acquire + bar.sync
 // order every later global read after the other CTAs' releases.
@@ -183,7 +244,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ph
 
 struct MegaSmem {
   uint8_t *stages;
-  uint4 *xq;        // [nb_max][4]
+  uint2 *xq;        // [4 planes p][nb_max] {signed bytes of lane 2p, of lane 2p+1} of every block
+  int nbx;          // plane stride = nb_max + 2 (bank-conflict padding)
   float *dxs;       // [nb_max]
   float *xs;        // [xs_floats] attention scores / probabilities
   float *rowres;    // [MEGA_MAX_ROWS]
@@ -221,9 +283,9 @@ __device__ __forceinline__ float mega_max_f(float v, float *redf, int buf, int t
 }
 
 // quantize_row_q4_0 (AVX2 branch, ggml.c:456-523) for one 32-block handled by 4 consecutive lanes (8 values each).
-// Writes the dp4a-ready form: xq[b][p] = {xs(lane 2p), xs(lane 2p+1), seed(lane 2p), seed(lane 2p+1)}, dxs[b] = d.
+// Writes the dp4a-ready form: plane p of xq gets {bytes of lane 2p, bytes of lane 2p+1} of block b, dxs[b] = d.
 // s = lane-quad index 0..3 of a live block, >= 4 for a padding thread (takes part in the shuffles, stores nothing).
-__device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s, uint4 *xq, float *dxs) {
+__device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s, uint2 *xq, int nbx, float *dxs) {
   float amax = 0.0f;
 #pragma unroll
   for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -237,24 +299,16 @@ __device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s
   // this thread holds elements 8s..8s+7 = one half (s>>1) of AVX lanes 4*(s&1)+j, j=0..3 (pairs q[2j], q[2j+1])
   const uint32_t hw01 = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
   const uint32_t hw23 = (uint32_t) (q[4] & 0xff) | ((uint32_t) (q[5] & 0xff) << 8) | ((uint32_t) (q[6] & 0xff) << 16) | ((uint32_t) (q[7] & 0xff) << 24);
-  const int sum01 = q[0] + q[1], sum11 = q[2] + q[3], sum23 = q[4] + q[5], sum33 = q[6] + q[7];
   const uint32_t o01 = __shfl_xor_sync(0xffffffffu, hw01, 2);
   const uint32_t o23 = __shfl_xor_sync(0xffffffffu, hw23, 2);
-  const int os0 = __shfl_xor_sync(0xffffffffu, sum01, 2), os1 = __shfl_xor_sync(0xffffffffu, sum11, 2);
-  const int os2 = __shfl_xor_sync(0xffffffffu, sum23, 2), os3 = __shfl_xor_sync(0xffffffffu, sum33, 2);
   if (s < 2) {
     // lanes 4s+0..3: low half-word = my elements (2l, 2l+1), high half-word = partner's (16+2l, 17+2l)
     const uint32_t x0 = (hw01 & 0xffffu) | (o01 << 16);
     const uint32_t x1 = (hw01 >> 16) | (o01 & 0xffff0000u);
     const uint32_t x2 = (hw23 & 0xffffu) | (o23 << 16);
     const uint32_t x3 = (hw23 >> 16) | (o23 & 0xffff0000u);
-    // dp4a accumulator seeds: 0x4B400000 is the bit pattern of 12582912.0f, so (seed + isum) IS the float 12582912+isum
-    const int c0 = 0x4B400000 - 8 * (sum01 + os0);      // even lane: low nibbles
-    const int c1 = 0x4B400000 - 128 * (sum11 + os1);    // odd lane: high nibbles carry a factor 16
-    const int c2 = 0x4B400000 - 8 * (sum23 + os2);
-    const int c3 = 0x4B400000 - 128 * (sum33 + os3);
-    xq[b * 4 + 2 * s + 0] = make_uint4(x0, x1, (uint32_t) c0, (uint32_t) c1);
-    xq[b * 4 + 2 * s + 1] = make_uint4(x2, x3, (uint32_t) c2, (uint32_t) c3);
+    xq[(2 * s + 0) * nbx + b] = make_uint2(x0, x1);
+    xq[(2 * s + 1) * nbx + b] = make_uint2(x2, x3);
     if (s == 0) dxs[b] = d;
   }
 }
@@ -265,19 +319,19 @@ __device__ __forceinline__ void quantize_block_4t(const float v[8], int b, int s
 // checked (one L2 latency when the data is already there), then every 16-byte half-pair is re-polled until both of its
 // sequence numbers match.  Threads past the end re-read the last item (harmless duplicates).
 template <int N>
-__device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int it0, uint32_t seq, long long limit,
+__device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int it0, int rot, uint32_t seq, long long limit,
                                                float (&v)[N][8], int tid) {
   uint4 r[N][4];
 #pragma unroll
   for (int rd = 0; rd < N; rd++) {
-    const int it = min(it0 + tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    const int it = rot_item(it0 + tid + rd * MEGA_COMPUTE_THREADS, items, rot);
     const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t) it * 8);
 #pragma unroll
     for (int i = 0; i < 4; i++) r[rd][i] = ld_vol_v4(p + i);
   }
 #pragma unroll
   for (int rd = 0; rd < N; rd++) {
-    const int it = min(it0 + tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    const int it = rot_item(it0 + tid + rd * MEGA_COMPUTE_THREADS, items, rot);
     const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t) it * 8);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -298,35 +352,38 @@ __device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int 
 __device__ __forceinline__ void zero_pad_blocks(int nb, const MegaSmem &sm, int tid) {
   const int nbp = (nb + 3) & ~3;
   if (tid < (nbp - nb) * 4) {
-    sm.xq[nb * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    sm.xq[(tid & 3) * sm.nbx + nb + (tid >> 2)] = make_uint2(0u, 0u);
     if ((tid & 3) == 0) sm.dxs[nb + (tid >> 2)] = 0.0f;
   }
 }
 
 // PLAIN: quantize x[K] (flagged words, polled) -> xq/dxs.
 template <int N>
-__device__ __forceinline__ void prologue_plain_batch(const uint2 *src, int items, int it0, uint32_t seq, long long limit,
+__device__ __forceinline__ void prologue_plain_batch(const uint2 *src, bool plain, int items, int it0, int rot, uint32_t seq, long long limit,
                                                      const MegaSmem &sm, int tid) {
   float v[N][8];
-  ll_read_rounds<N>(src, items, it0, seq, limit, v, tid);
+  if (plain) plain_read_rounds<N>(reinterpret_cast<const float *>(src), items, it0, rot, v, tid);
+  else ll_read_rounds<N>(src, items, it0, rot, seq, limit, v, tid);
 #pragma unroll
   for (int rd = 0; rd < N; rd++) {
     const int it = it0 + tid + rd * MEGA_COMPUTE_THREADS;
     const bool live = it < items;         // a block's 4 quarter-items are all live or all padding (512 % 4 == 0)
-    const int iq = live ? it : items - 1;
-    quantize_block_4t(v[rd], iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+    const int iq = rot_item(it, items, rot);
+    quantize_block_4t(v[rd], iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.nbx, sm.dxs);
   }
 }
 
-__device__ __forceinline__ void prologue_plain(const uint2 *src, int nb, uint32_t seq, long long limit, const MegaSmem &sm, int tid) {
+// src: flagged words (plain == false) or the same area used as a plain f32 vector (plain == true)
+__device__ __forceinline__ void prologue_plain(const uint2 *src, bool plain, int nb, uint32_t seq, long long limit, const MegaSmem &sm, int tid) {
   const int items = nb * 4;
   const int rounds = (items + MEGA_COMPUTE_THREADS - 1) / MEGA_COMPUTE_THREADS;
+  const int rot = B200_ROTATE ? 4 * (int) (((long long) blockIdx.x * nb) / gridDim.x) : 0;   // whole blocks
   for (int r0 = 0; r0 < rounds; r0 += 3) {     // at most 3 rounds (12 x 16 B per thread) in flight at a time
     const int n = rounds - r0;
     const int it0 = r0 * MEGA_COMPUTE_THREADS;
-    if (n >= 3) prologue_plain_batch<3>(src, items, it0, seq, limit, sm, tid);
-    else if (n == 2) prologue_plain_batch<2>(src, items, it0, seq, limit, sm, tid);
-    else prologue_plain_batch<1>(src, items, it0, seq, limit, sm, tid);
+    if (n >= 3) prologue_plain_batch<3>(src, plain, items, it0, rot, seq, limit, sm, tid);
+    else if (n == 2) prologue_plain_batch<2>(src, plain, items, it0, rot, seq, limit, sm, tid);
+    else prologue_plain_batch<1>(src, plain, items, it0, rot, seq, limit, sm, tid);
   }
   zero_pad_blocks(nb, sm, tid);
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
@@ -382,7 +439,7 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) v[i] = __fmul_rn(w[i], __fmul_rn((float) xd[rd][i], nscale));   // y = (float)v; y *= scale; w*y
-      quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.dxs);
+      quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.nbx, sm.dxs);
     }
   }
   zero_pad_blocks(nb, sm, tid);
@@ -390,17 +447,19 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
 }
 
 // fill the register copy of a flagged activation vector (polled)
-__device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], const uint2 *src, int nb, uint32_t seq,
+__device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], const uint2 *src, bool plain, int nb, uint32_t seq,
                                            long long limit, int tid) {
   const int items = nb * 4;
   float v[MEGA_NORM_ROUNDS][8];
-  if (items <= MEGA_COMPUTE_THREADS) {
+  if (plain) {
+    plain_read_rounds<MEGA_NORM_ROUNDS>(reinterpret_cast<const float *>(src), items, 0, 0, v, tid);
+  } else if (items <= MEGA_COMPUTE_THREADS) {
     float v1[1][8];
-    ll_read_rounds<1>(src, items, 0, seq, limit, v1, tid);
+    ll_read_rounds<1>(src, items, 0, 0, seq, limit, v1, tid);
 #pragma unroll
     for (int i = 0; i < 8; i++) { v[0][i] = v1[0][i]; v[1][i] = 0.0f; }
   } else {
-    ll_read_rounds<MEGA_NORM_ROUNDS>(src, items, 0, seq, limit, v, tid);
+    ll_read_rounds<MEGA_NORM_ROUNDS>(src, items, 0, 0, seq, limit, v, tid);
   }
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
@@ -411,16 +470,6 @@ __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], co
 }
 
 // ---- GEMV main loop over this CTA's rows of one matrix; leaves the row results in sm.rowres -------------------------
-#ifndef B200_EVICT_FIRST
-#define B200_EVICT_FIRST 1  // weight stream marked evict_first in L2 (read once per token)
-#endif
-#ifndef B200_HINTS
-#define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
-#endif
-#ifndef B200_NO_MATH
-#define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
-#endif
-
 // Position in the ring of stages: stage index and the parity of its mbarrier phase, advanced without div/mod.
 struct RingPos {
   int s;
@@ -429,66 +478,52 @@ struct RingPos {
   __device__ __forceinline__ void next(int S) { g++; if (++s == S) { s = 0; par ^= 1u; } }
 };
 
-template <int LP>
+template <int LP, int RPT>
 __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                           int S, int stage_bytes, int tid) {
   constexpr int UPR = 4 / LP;
   const int R = rp.R, cb = md.cb;
+  const int G = R / RPT;                                // thread (g, t) owns rows g, g + G, ... (R is a multiple of 4)
   const int nbq = (md.nb + 3) >> 2, cq = cb >> 2;
   const int nchunks = (nbq + cq - 1) / cq;
-  const bool active = tid < R * UPR;
-  const int r = active ? tid / UPR : R - 1;
+  const bool active = tid < G * UPR;
+  const int g = active ? tid / UPR : G - 1;
   const int t = tid % UPR;
-  u64 acc[LP];
+  u64 acc[RPT][LP];
 #pragma unroll
-  for (int j = 0; j < LP; j++) acc[j] = pack_f2(0.0f, 0.0f);
-  const u64 cvt_mul = pack_f2(1.0f, 0.0625f);
-  const u64 cvt_sub = pack_f2(-12582912.0f, -786432.0f);
-  const bool warp_active = (tid & ~31) < R * UPR;     // warps with no rows skip the math but still release stages
+  for (int i = 0; i < RPT; i++)
+#pragma unroll
+    for (int j = 0; j < LP; j++) acc[i][j] = pack_f2(0.0f, 0.0f);
+  const bool warp_active = (tid & ~31) < G * UPR;     // warps with no rows skip the math but still release stages
 
   for (int k = 0; k < nchunks; k++, ring.next(S)) {
     const int s = ring.s;
     mbar_wait(&sm.full[s], ring.par);
     if (warp_active && !B200_NO_MATH) {
       const int cqk = min(cq, nbq - k * cq);
-      gemv_chunk<LP>(sm.stages + (size_t) s * stage_bytes, cqk, R, r, t, sm.xq + k * cb * 4 + t * LP, sm.dxs + k * cb,
-                     acc, cvt_mul, cvt_sub);
+      gemv_chunk<LP, RPT>(sm.stages + (size_t) s * stage_bytes, cqk, R, g, t, sm.xq, sm.dxs, sm.nbx, k * cb, acc);
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
   }
-
-  // horizontal sum exactly as ggml.c:1461-1466: (acc[k]+acc[k+4]) k<4, then (r0+r2)+(r1+r3)
-  float lane[2 * LP];
 #pragma unroll
-  for (int j = 0; j < LP; j++) unpack_f2(acc[j], lane[2 * j], lane[2 * j + 1]);
-  float res;
-  if constexpr (LP == 4) {
-    const float r0 = __fadd_rn(lane[4], lane[0]), r1 = __fadd_rn(lane[5], lane[1]);
-    const float r2 = __fadd_rn(lane[6], lane[2]), r3 = __fadd_rn(lane[7], lane[3]);
-    res = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-  } else if constexpr (LP == 2) {
-    float rr[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) rr[i] = __fadd_rn(lane[i], __shfl_xor_sync(0xffffffffu, lane[i], 1));
-    res = __fadd_rn(__fadd_rn(rr[0], rr[2]), __fadd_rn(rr[1], rr[3]));
-  } else {
-    const float t0 = __fadd_rn(lane[0], __shfl_xor_sync(0xffffffffu, lane[0], 2));
-    const float t1 = __fadd_rn(lane[1], __shfl_xor_sync(0xffffffffu, lane[1], 2));
-    const float s0 = __fadd_rn(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
-    const float s1 = __fadd_rn(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
-    res = __fadd_rn(s0, s1);
+  for (int i = 0; i < RPT; i++) {
+    const float res = row_hsum<LP>(acc[i]);
+    if (active && t == 0) sm.rowres[g + i * G] = res;
   }
-  if (active && t == 0) sm.rowres[r] = res;
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
 __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                               int S, int stage_bytes, int tid) {
-  switch (md.lp) {
-    case 1: gemv_rows<1>(md, rp, sm, ring, S, stage_bytes, tid); break;
-    case 2: gemv_rows<2>(md, rp, sm, ring, S, stage_bytes, tid); break;
-    default: gemv_rows<4>(md, rp, sm, ring, S, stage_bytes, tid); break;
+  const int rpt = (rp.R % md.rpt == 0) ? md.rpt : 1;   // R is a multiple of 4, so 2 and 4 always divide it
+  switch (md.lp * 8 + rpt) {
+    case 1 * 8 + 1: gemv_rows<1, 1>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    case 1 * 8 + 2: gemv_rows<1, 2>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    case 1 * 8 + 4: gemv_rows<1, 4>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    case 2 * 8 + 1: gemv_rows<2, 1>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    case 2 * 8 + 2: gemv_rows<2, 2>(md, rp, sm, ring, S, stage_bytes, tid); break;
+    default: gemv_rows<4, 1>(md, rp, sm, ring, S, stage_bytes, tid); break;
   }
 }
 
@@ -598,9 +633,15 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   if (warp == 0) {
     float o = sm.part[lane];
     for (int t = 1; t < nth; t++) o = __fadd_rn(o, sm.part[t * 32 + lane]);
-    ll_bcast(a.tp.ll, a.tp.size, att_off + h * HD + qr * 32 + lane, o, seq);      // KQV_merged, PO.mm:641-646 -> every GPU
-    __syncwarp();
-    if (lane == 0) hint_arrive(a.tp.hint, a.tp.size, HINT_ATT);
+    if (B200_PLAIN_LOCAL && a.tp.size == 1) {
+      __stcg(reinterpret_cast<float *>(a.tp.ll[0] + att_off) + h * HD + qr * 32 + lane, o);   // KQV_merged, PO.mm:641-646
+      __syncwarp();
+      if (lane == 0) plain_arrive(a.tp.hint[0] + HINT_ATT);
+    } else {
+      ll_bcast(a.tp.ll, a.tp.size, att_off + h * HD + qr * 32 + lane, o, seq);    // ... -> every GPU of the group
+      __syncwarp();
+      if (lane == 0) hint_arrive(a.tp.hint, a.tp.size, HINT_ATT);
+    }
   }
 }
 
@@ -611,8 +652,10 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   const int nb_max = ((max(a.n_embd, a.n_ff) / 32) + 3) & ~3;   // whole quads
   MegaSmem sm;
   sm.stages = smem_mega;
-  sm.xq = reinterpret_cast<uint4 *>(smem_mega + (size_t) S * a.stage_bytes);
-  sm.dxs = reinterpret_cast<float *>(sm.xq + (size_t) nb_max * 4);
+  sm.xq = reinterpret_cast<uint2 *>(smem_mega + (size_t) S * a.stage_bytes);
+  sm.nbx = nb_max + 2;      // plane stride padded by 16 bytes: the 4 planes a quarter-warp reads together fall into
+                            // different banks (an unpadded power-of-two stride made every activation load a 4-way conflict)
+  sm.dxs = reinterpret_cast<float *>(sm.xq + (size_t) sm.nbx * 4);
   sm.xs = sm.dxs + nb_max;
   sm.rowres = sm.xs + a.xs_floats;
   sm.redd = reinterpret_cast<double *>(sm.rowres + MEGA_MAX_ROWS);
@@ -725,6 +768,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // arrival-hint counters never reset: before this launch every buffer kind saw (epoch-1)*n_layer rounds of arrivals
   const unsigned int *const hint_me = a.tp.hint[rank];
   const unsigned int rounds0 = (epoch - 1u) * (unsigned int) a.n_layer;
+  // one GPU: plain f32 words in the first half of each region + authoritative counters (see plain_wait)
+  const bool plain = B200_PLAIN_LOCAL && T == 1;     // att, h
+  const bool plain_x = B200_PLAIN_X && T == 1;       // inpL, inpFF
+  unsigned int *const cnt_me = a.tp.hint[rank];
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
   unsigned int phase = 0;
@@ -750,21 +797,26 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
     if (rp.R == 0) {
       // no rows of this matrix on this CTA (tensor-parallel shards can have fewer row granules than SMs)
-      PROF_MARK(); PROF_MARK(); PROF_MARK();
+      PROF_MARK(); PROF_MARK(); PROF_MARK(); PROF_MARK();
       if (kind == PH_QKV) { grid_barrier(a.bar, phase, tid, limit); PROF_MARK(); }
       continue;
     }
 
     // ---- prologue ----
     if (kind == PH_WO) {
-      if (B200_HINTS) hint_wait(hint_me + HINT_ATT, (rounds0 + il + 1u) * a.tp.p_att, limit, tid);
-      prologue_plain(ll_me + o_att + par * E, E / 32, seq, limit, sm, tid);     // PO.mm:649-651
+      if (plain) plain_wait(hint_me + HINT_ATT, (rounds0 + il + 1u) * a.tp.p_att, limit, tid);
+      else if (B200_HINTS) hint_wait(hint_me + HINT_ATT, (rounds0 + il + 1u) * a.tp.p_att, limit, tid);
+      PROF_MARK();
+      prologue_plain(ll_me + o_att + par * E, plain, E / 32, seq, limit, sm, tid);     // PO.mm:649-651
     } else if (kind == PH_W2) {
-      if (B200_HINTS) hint_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
-      prologue_plain(ll_me + o_h + par * F, F / 32, seq, limit, sm, tid);       // PO.mm:682-684
+      if (plain) plain_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
+      else if (B200_HINTS) hint_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
+      PROF_MARK();
+      prologue_plain(ll_me + o_h + par * F, plain, F / 32, seq, limit, sm, tid);       // PO.mm:682-684
     } else {
       double xd[MEGA_NORM_ROUNDS][8];
       if (step == 0) {
+        PROF_MARK();
         // get_rows: dequantize_row_q4_0 of the token's embedding row (ggml.c:6760-6785, 651-684) straight into registers
         const uint8_t *row = a.tok_emb + (size_t) a.sp->token * (E / 32) * 20;
         const int items = E / 8;
@@ -780,7 +832,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
               const int qn = (by >> (4 * i)) & 0xf;             // element 2j = low nibble of byte j, 2j+1 = high nibble
               const float v = __fmul_rn((float) (qn - 8), d);
               xd[rd][i] = v;
-              if (blockIdx.x == 0) ll_store(ll_me + o_inpL + it * 8 + i, v, seq0);   // residual source of layer 0 (this GPU only)
+              if (blockIdx.x == 0) {                            // residual source of layer 0 (this GPU only)
+                if (plain_x) __stcg(reinterpret_cast<float *>(ll_me + o_inpL) + it * 8 + i, v);   // ordered by the qkv -> attention barrier
+                else ll_store(ll_me + o_inpL + it * 8 + i, v, seq0);
+              }
             }
           } else {
 #pragma unroll
@@ -790,16 +845,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
       } else {
         // inpFF(l) is round rounds0+l+1 of its counter; inpL(l), l >= 1, is round rounds0+l of its own (layer 0's input
         // is the embedding row: no arrival)
-        if (B200_HINTS) {
-          if (kind == PH_W13) hint_wait(hint_me + HINT_INPFF, (rounds0 + il + 1u) * a.tp.p_e, limit, tid);
-          else hint_wait(hint_me + HINT_INPL, (rounds0 + il) * a.tp.p_e, limit, tid);
-        }
-        load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, E / 32, seq, limit, tid);
+        const unsigned int *cnt = hint_me + (kind == PH_W13 ? HINT_INPFF : HINT_INPL);
+        const unsigned int expected = (rounds0 + il + (kind == PH_W13 ? 1u : 0u)) * a.tp.p_e;
+        if (plain_x) plain_wait(cnt, expected, limit, tid);
+        else if (B200_HINTS) hint_wait(cnt, expected, limit, tid);
+        PROF_MARK();
+        load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, plain_x, E / 32, seq, limit, tid);
       }
       const float *nw = kind == PH_QKV ? L.attn_norm : kind == PH_W13 ? L.ffn_norm : a.final_norm;
       prologue_norm_regs(xd, nw, E / 32, sm, tid);                              // PO.mm:570-575, 660-665, 694-701
     }
     PROF_MARK();
+
+    // the residual this thread's row will need (PO.mm:654, 687) has been there since an earlier phase: fetch it now,
+    // under the row loop, instead of paying an L2 round trip in the epilogue (R <= 512: one row per thread)
+    float resid = 0.0f;
+    if ((kind == PH_WO || kind == PH_W2) && tid < rp.R && rp.row0 + tid < md.M) {
+      const uint2 *rsrc = ll_me + (kind == PH_WO ? o_inpL : o_inpFF) + par * E;
+      resid = plain_x ? __ldcg(reinterpret_cast<const float *>(rsrc) + c0 + rp.row0 + tid) : ll_wait1(rsrc + c0 + rp.row0 + tid, seq, limit);
+    }
 
     // ---- the mat-vec ----
     gemv_dispatch(md, rp, sm, gchunk, S, stage_bytes, tid);
@@ -833,10 +897,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         if (2 * g < md.M) {
           const uint16_t hx = __half_as_ushort(__float2half_rn(sm.rowres[2 * i]));
           const float sv = __half2float(__ushort_as_half(__ldg(a.silu_table + hx)));
-          ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, __fmul_rn(sv, sm.rowres[2 * i + 1]), seq);
+          const float hv = __fmul_rn(sv, sm.rowres[2 * i + 1]);
+          if (plain) __stcg(reinterpret_cast<float *>(ll_me + o_h + par * F) + g, hv);
+          else ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, hv, seq);
         }
       }
-      if (B200_HINTS) {
+      if (plain) {
+        named_bar_sync(1, MEGA_COMPUTE_THREADS);
+        if (tid == 0) plain_arrive(cnt_me + HINT_H);
+      } else if (B200_HINTS) {
         named_bar_sync(1, MEGA_COMPUTE_THREADS);
         if (tid == 0) hint_arrive(a.tp.hint, T, HINT_H);
       }
@@ -851,18 +920,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
       }
     } else {
       // ggml_add with the residual stream (PO.mm:654, 687).  wo: inpFF(l) = wo.att + inpL(l); w2: inpL(l+1) = w2.h + inpFF(l).
-      // The residual words were validated by this CTA's own earlier prologue; the poll is a formality.
-      const uint32_t o_res = (kind == PH_WO ? o_inpL : o_inpFF) + par * E;
       const uint32_t o_dst = kind == PH_WO ? o_inpFF + par * E : o_inpL + (par ^ 1u) * E;
       const uint32_t seq_dst = kind == PH_WO ? seq : seq + 1u;
-      for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
-        const int g = rp.row0 + i;
-        if (g < md.M) {
-          const float r = ll_wait1(ll_me + o_res + c0 + g, seq, limit);
-          ll_bcast(a.tp.ll, T, o_dst + c0 + g, __fadd_rn(sm.rowres[i], r), seq_dst);
-        }
+      if (tid < rp.R && rp.row0 + tid < md.M) {
+        const int g = rp.row0 + tid;
+        const float v = __fadd_rn(sm.rowres[tid], resid);
+        if (plain_x) __stcg(reinterpret_cast<float *>(ll_me + o_dst) + c0 + g, v);
+        else ll_bcast(a.tp.ll, T, o_dst + c0 + g, v, seq_dst);
       }
-      if (B200_HINTS) {
+      if (plain_x) {
+        named_bar_sync(1, MEGA_COMPUTE_THREADS);
+        if (tid == 0) plain_arrive(cnt_me + (kind == PH_WO ? HINT_INPFF : HINT_INPL));
+      } else if (B200_HINTS) {
         named_bar_sync(1, MEGA_COMPUTE_THREADS);
         if (tid == 0) hint_arrive(a.tp.hint, T, kind == PH_WO ? HINT_INPFF : HINT_INPL);
       }

@@ -26,6 +26,11 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
 
+// signed bytes (a) x signed bytes (b) + c  (SASS IDP.4A.S8.S8)
+__device__ __forceinline__ int dp4a_ss(int a, int b, int c) {
+  int d; asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -8 gpurun_out/pytest_gpu.log
+timeout 600 python -c "import bench; bench.ensure_model(32)" > gpurun_out/model.log 2>&1
+ln -sf /tmp/b200_bench/ggml-model-q4_0.bin /tmp/probe-7b-l32.bin
+P="timeout 300 python tools/probe.py --layers 32 --steps 64"
+rm -f gpurun_out/ab.log
+echo "== new" >> gpurun_out/ab.log; $P 2>&1 | grep -E "decode|rror" | tail -1 >> gpurun_out/ab.log
+for e in "B200_LP_QKV=12" "B200_LP_QKV=2" "B200_LP_W13=22" "B200_LP_W13=12" "B200_LP_SMALL=12" "B200_LP_OUT=22" "B200_LP_QKV=12 B200_LP_W13=22" "B200_STAGE_BYTES=49152" "B200_STAGE_BYTES=65536"; do
+  echo "== new $e" >> gpurun_out/ab.log
+  env $e $P 2>&1 | grep -E "decode|rror" | tail -1 >> gpurun_out/ab.log
+done
+cat gpurun_out/ab.log
+timeout 300 python tools/phase_profile.py --layers 8 --pos 64 > gpurun_out/phase.log 2>&1; tail -24 gpurun_out/phase.log

@@ -25,7 +25,7 @@ toks, _, ms = m.decode_device(8, 5, args.pos - 8, n_threads=8)     # fill the ca
 print(f"decode {args.pos - 8} steps: {ms / (args.pos - 8) * 1e3:.1f} us/token")
 L = lsb.lib()
 L.b200_llama_profile_token.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
-cap = 148 * (2 + 15 * args.layers + 4) + 1024
+cap = 148 * (2 + 20 * args.layers + 8) + 1024
 buf = np.zeros(cap, dtype=np.int64)
 ncta = C.c_int(0)
 for rep in range(3):
@@ -35,11 +35,13 @@ t = buf[: ncta.value * marks].reshape(ncta.value, marks).astype(np.float64)
 t = (t - t[:, 0].min()) / 1e3   # us
 # marks per layer (megakernel.cuh): qkv {prologue = wait for inpL + LayerNorm + quantize, rows, epilogue, local barrier},
 # attention, then {prologue = wait for the flagged activation words + quantize, rows, epilogue = flagged stores} x 3
-names = ["qkv wait+norm+quant", "qkv rows", "qkv epilogue", "barrier (qkv->attn)", "attention", "wo wait+quant", "wo rows",
-         "wo epilogue", "w13 wait+norm+quant", "w13 rows", "w13 epilogue", "w2 wait+quant", "w2 rows", "w2 epilogue"]
+names = ["qkv wait (arrival)", "qkv read+norm+quant", "qkv rows", "qkv epilogue", "barrier (qkv->attn)", "attention",
+         "wo wait (arrival)", "wo read+quant", "wo rows", "wo epilogue",
+         "w13 wait (arrival)", "w13 read+norm+quant", "w13 rows", "w13 epilogue",
+         "w2 wait (arrival)", "w2 read+quant", "w2 rows", "w2 epilogue"]
 NM = len(names)
 nl = args.layers
-print(f"layers {nl} pos {args.pos}: kernel span {t[:, NM * nl + 3].max():.1f} us; "
+print(f"layers {nl} pos {args.pos}: kernel span {t[:, NM * nl + 4].max():.1f} us; "
       f"per layer {(t[:, NM * nl].max() - t[:, 0].min()) / nl:.2f} us")
 seg = np.zeros((nl, NM, ncta.value))
 for il in range(nl):
@@ -52,6 +54,6 @@ for k, n in enumerate(names):
     print(f"{n:>22}: median CTA {med:6.2f} us   slowest CTA {mx:6.2f} us   fastest {mn:6.2f} us")
 print(f"{'sum of medians':>22}: {sum(np.median(seg[1:, k, :]) for k in range(NM)):.2f} us/layer")
 o = NM * nl
-print(f"output: prologue {np.median(t[:, o + 1] - t[:, o]):.2f}  rows {np.median(t[:, o + 2] - t[:, o + 1]):.2f}  store {np.median(t[:, o + 3] - t[:, o + 2]):.2f} us (median CTA)")
+print(f"output: wait {np.median(t[:, o + 1] - t[:, o]):.2f}  read+norm+quant {np.median(t[:, o + 2] - t[:, o + 1]):.2f}  rows {np.median(t[:, o + 3] - t[:, o + 2]):.2f}  store {np.median(t[:, o + 4] - t[:, o + 3]):.2f} us (median CTA)")
 if args.out:
     np.save(args.out, t)
