@@ -738,9 +738,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   CUDA_TRY(cudaMalloc(&m->d_q, E * 4));
   CUDA_TRY(cudaMalloc(&m->d_att, E * 4));
   CUDA_TRY(cudaMalloc(&m->d_h, (size_t) F * 4));
-  // exchange area: flagged activations inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F] (8 B per value), then the logits,
+  // exchange area: flagged activations inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F] | qkv[2][3E] (8 B per value), then the logits,
   // then the end-of-token flags and the arrival-hint counters.  One allocation = one IPC handle; zero-filled, so no flag matches a live sequence number.
-  m->xchg_ll_bytes = ((size_t) 6 * E + (size_t) 2 * F) * 8;
+  m->xchg_ll_bytes = ((size_t) 12 * E + (size_t) 2 * F) * 8;
   m->xchg_bytes = m->xchg_ll_bytes + (size_t) V * 4 + MEGA_MAX_TP * 4 + 4 * 4 + 256;
   CUDA_TRY(cudaMalloc(&m->d_xchg, m->xchg_bytes));
   CUDA_TRY(cudaMemset(m->d_xchg, 0, m->xchg_bytes));
@@ -774,7 +774,7 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
     const size_t fixed = (size_t) (nb_max + 2) * 32 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
-                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + MEGA_COMPUTE_WARPS * 4;
+                         MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + 288 * 4 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;

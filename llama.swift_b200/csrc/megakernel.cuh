@@ -33,6 +33,9 @@
 #ifndef B200_ROTATE
 #define B200_ROTATE 0       // (measured: 3.5 % SLOWER) every CTA starts its sweep over an activation vector at a different block (spreads the
 #endif                      // 148-fold re-read of the same lines over the L2 slices)
+#ifndef B200_ATT_KB
+#define B200_ATT_KB 8       // K.Q: positions per warp batch (12 and 16 measured slower: register pressure)
+#endif
 #ifndef B200_HINTS
 #define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
 #endif
@@ -147,6 +150,7 @@ __device__ __forceinline__ float ll_wait1(const uint2 *p, uint32_t seq, long lon
   if (r.y != seq) {
     const long long t0 = clock64();
     do {
+      __nanosleep(20);
       r = ld_vol_v2(p);
       if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
     } while (r.y != seq);
@@ -223,25 +227,6 @@ __device__ __forceinline__ void plain_read_rounds(const float *src, int items, i
   }
 }
 
-// Grid barrier for the compute warps (the loader warp never joins: it only obeys the ring).
-// bar.sync orders every compute thread's global writes before thread 0's gpu-scope release; the acquire + bar.sync
-// order every later global read after the other CTAs' releases.
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &phase, int tid, long long limit) {
-  named_bar_sync(1, MEGA_COMPUTE_THREADS);
-  phase++;
-  if (tid == 0) {
-    red_release_add_u32(bar, 1u);
-    const unsigned int target = phase * gridDim.x;
-    if (ld_acquire_u32(bar) < target) {
-      const long long t0 = clock64();
-      while (ld_acquire_u32(bar) < target) {
-        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
-      }
-    }
-  }
-  named_bar_sync(1, MEGA_COMPUTE_THREADS);
-}
-
 struct MegaSmem {
   uint8_t *stages;
   uint2 *xq;        // [4 planes p][nb_max] {signed bytes of lane 2p, of lane 2p+1} of every block
@@ -253,6 +238,7 @@ struct MegaSmem {
   float *redf;      // [2][16]
   float *part;      // [MEGA_MAX_NTH][32]
   double2 *ropev;   // [head_dim/2] (cos, sin) of this token's position, fetched once at kernel start
+  float *qkc;       // [288] this token's q (128), k (128) of the head and v (32) of the head quarter, for the attention phase
   uint64_t *full, *empty;
 };
 
@@ -529,17 +515,45 @@ __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart r
 
 // ---- attention phase for (head h, output quarter qr): K.Q for all positions, soft_max, V.P for 32 dims --------------
 __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerDesc &L, const MegaSmem &sm, int h, int qr,
-                                                int pos, int p_part, uint32_t att_off, uint32_t seq, int tid) {
+                                                int pos, int p_part, uint32_t att_off, const uint2 *qkv_ll, uint32_t seq,
+                                                long long limit, int tid) {
   constexpr int HD = 128, NW = MEGA_COMPUTE_WARPS;
   const int lane = tid & 31, warp = tid >> 5;
   const int E = a.n_embd;
   const int p_valid = pos + 1;      // diag_mask_inf: columns > n_past + i are -inf -> probability 0 (ggml.c:6946-6953)
   float *sc = sm.xs;
-  float qv[4];
+  // This token's roped Q, its K row and V row arrive as flagged words straight from the CTAs that computed them (no
+  // grid barrier between the mat-vec and the attention); rows of earlier positions come from the f32 cache, whose
+  // current row is written for FUTURE tokens only.
+  // One warp polls (288 words), the other 15 sleep in the barrier: polling threads compete with the weight stream for L2.
+  if (warp == 0) {
+    const uint2 *src[9];
 #pragma unroll
-  for (int i = 0; i < 4; i++) qv[i] = __ldcg(a.q + h * HD + lane + 32 * i);
+    for (int i = 0; i < 4; i++) { src[i] = qkv_ll + h * HD + lane + 32 * i; src[4 + i] = qkv_ll + E + h * HD + lane + 32 * i; }
+    src[8] = qkv_ll + 2 * E + h * HD + qr * 32 + lane;
+    uint2 w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = ld_vol_v2(src[i]);          // all nine in flight: one L2 round trip when the data is there
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      if (w[i].y != seq) {
+        const long long t0 = clock64();
+        do {
+          __nanosleep(20);
+          w[i] = ld_vol_v2(src[i]);
+          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+        } while (w[i].y != seq);
+      }
+      sm.qkc[i < 8 ? (i < 4 ? 0 : 128) + lane + 32 * (i & 3) : 256 + lane] = __uint_as_float(w[i].x);
+    }
+  }
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
+  float qv[4], kcur[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { qv[i] = sm.qkc[lane + 32 * i]; kcur[i] = sm.qkc[128 + lane + 32 * i]; }
+  const float vcur = sm.qkc[256 + lane];
   // K.Q: ggml_vec_dot_f32, AVX mapping (lane t = 8*vec + l owns elements t, t+32, t+64, t+96), ggml.c:1223-1258, 872-887
-  constexpr int KB = 8;     // positions per batch: 32 independent loads in flight per lane
+  constexpr int KB = B200_ATT_KB;     // positions per batch: 4*KB independent loads in flight per lane
   for (int j0 = warp * KB; j0 < p_valid; j0 += NW * KB) {
     float kk[KB][4];
 #pragma unroll
@@ -547,7 +561,10 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
       const int j = min(j0 + u, p_valid - 1);
       const float *kp = L.k_layer + (size_t) j * E + h * HD + lane;
 #pragma unroll
-      for (int i = 0; i < 4; i++) kk[u][i] = __ldcg(kp + 32 * i);
+      for (int i = 0; i < 4; i++) {
+        const float kc = __ldcg(kp + 32 * i);
+        kk[u][i] = j == pos ? kcur[i] : kc;
+      }
     }
 #pragma unroll
     for (int u = 0; u < KB; u++) {
@@ -573,7 +590,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     const int j0 = warp * dc;
     const int j1 = warp < nth ? min(min(j0 + dc, p_part), p_valid) : j0;
 #pragma unroll
-    for (int i = 0; i < VB; i++) vpre[i] = (j0 + i < j1) ? __ldcg(vp + (size_t) (j0 + i) * E) : 0.0f;
+    for (int i = 0; i < VB; i++) vpre[i] = (j0 + i < j1) ? (j0 + i == pos ? vcur : __ldcg(vp + (size_t) (j0 + i) * E)) : 0.0f;
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
   // soft_max, ggml.c:7019-7041
@@ -606,14 +623,14 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     for (; j + 16 <= j1; j += 16) {
       float vv[16];
 #pragma unroll
-      for (int i = 0; i < 16; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
+      for (int i = 0; i < 16; i++) { const float vc = __ldcg(vp + (size_t) (j + i) * E); vv[i] = j + i == pos ? vcur : vc; }
 #pragma unroll
       for (int i = 0; i < 16; i++) acc = fmaf(vv[i], sc[j + i], acc);           // vec_mad_f32, ggml.c:1696
     }
     if (j + 8 <= j1) {
       float vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
+      for (int i = 0; i < 8; i++) { const float vc = __ldcg(vp + (size_t) (j + i) * E); vv[i] = j + i == pos ? vcur : vc; }
 #pragma unroll
       for (int i = 0; i < 8; i++) acc = fmaf(vv[i], sc[j + i], acc);
       j += 8;
@@ -621,12 +638,19 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     if (j + 4 <= j1) {
       float vv[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) vv[i] = __ldcg(vp + (size_t) (j + i) * E);
+      for (int i = 0; i < 4; i++) { const float vc = __ldcg(vp + (size_t) (j + i) * E); vv[i] = j + i == pos ? vcur : vc; }
 #pragma unroll
       for (int i = 0; i < 4; i++) acc = fmaf(vv[i], sc[j + i], acc);
       j += 4;
     }
-    for (; j < j1; j++) acc = fmaf(__ldcg(vp + (size_t) j * E), sc[j], acc);
+    if (j < j1) {     // up to 3 positions left: their loads go out together, the fmaf chain stays in order
+      float vv[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) vv[i] = j + i < j1 ? (j + i == pos ? vcur : __ldcg(vp + (size_t) (j + i) * E)) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (j + i < j1) acc = fmaf(vv[i], sc[j + i], acc);
+    }
     sm.part[t * 32 + lane] = acc;
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
@@ -662,7 +686,8 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   sm.redf = reinterpret_cast<float *>(sm.redd + 32);
   sm.part = sm.redf + 32;
   sm.ropev = reinterpret_cast<double2 *>(sm.part + MEGA_MAX_NTH * 32);
-  sm.full = reinterpret_cast<uint64_t *>(sm.ropev + 64);
+  sm.qkc = reinterpret_cast<float *>(sm.ropev + 64);
+  sm.full = reinterpret_cast<uint64_t *>(sm.qkc + 288);
   sm.empty = sm.full + S;
   return sm;
 }
@@ -761,9 +786,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   // buffers); epoch >= 1 and never repeats, so a stale word of an earlier token can never match
   const uint32_t epoch = ld_vol_u32(a.epoch);
   const uint32_t seq0 = epoch * (uint32_t) (a.n_layer + 2) + 1u;
-  // flagged area (uint2 units): inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F]; the buffer alternates with the layer
+  // flagged area (uint2 units): inpL[2][E] | inpFF[2][E] | att[2][E] | h[2][F] | qkv[2][3E]; the buffer alternates with the layer
   // parity so a fast producer of layer l+1 can never overwrite words a slow consumer of layer l still polls
-  const uint32_t o_inpL = 0u, o_inpFF = 2u * E, o_att = 4u * E, o_h = 6u * E;
+  const uint32_t o_inpL = 0u, o_inpFF = 2u * E, o_att = 4u * E, o_h = 6u * E, o_qkv = 6u * E + 2u * F;   // qkv[2][3E]: this GPU only
   uint2 *const ll_me = a.tp.ll[rank];
   // arrival-hint counters never reset: before this launch every buffer kind saw (epoch-1)*n_layer rounds of arrivals
   const unsigned int *const hint_me = a.tp.hint[rank];
@@ -774,7 +799,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   unsigned int *const cnt_me = a.tp.hint[rank];
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
-  unsigned int phase = 0;
   int pm = 0;
   PROF_MARK();   // 0: kernel start
   const int n_steps = 5 * a.n_layer + 1;
@@ -785,10 +809,31 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const uint32_t seq = seq0 + (uint32_t) il;
     const uint32_t par = (uint32_t) il & 1u;
 
+    if (kind == PH_QKV && (int) blockIdx.x < 4 * nh_loc && pos > 0) {
+      // The K/V rows of earlier positions that this CTA's attention phase will read were written many tokens ago and have
+      // left L2 (the cache is 1 MB per position at 7B): start pulling them from HBM now, a whole mat-vec phase early.
+      // K rows of the head are shared by its 4 CTAs (each takes every 4th position, 4 lines per row); V: this CTA's
+      // 32-dim quarter of every row (1 line).
+      const int hh = rank * nh_loc + ((int) blockIdx.x >> 2), qq = (int) blockIdx.x & 3;
+      const float *kb = L.k_layer + hh * HD, *vb = L.v_layer + hh * HD + qq * 32;
+      const int nk = ((pos + 3 - qq) >> 2) * 4;          // (positions j = qq, qq+4, ... < pos) x 4 lines
+      for (int i = tid; i < nk + pos; i += MEGA_COMPUTE_THREADS) {
+        const float *pl = i < nk ? kb + (size_t) (qq + 4 * (i >> 2)) * E + (i & 3) * 32 : vb + (size_t) (i - nk) * E;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+      }
+    }
+    if (kind == PH_QKV && tid < 2) {
+      // next layer's LayerNorm weights (read once per token, so never in L2): start the HBM fetch a whole layer early
+      const float *nwp = il + 1 < a.n_layer ? (tid == 0 ? a.layers[il + 1].attn_norm : a.layers[il + 1].ffn_norm)
+                                            : (tid == 0 ? a.final_norm : nullptr);
+      if (nwp)
+        for (int line = blockIdx.x; line * 32 < E; line += gridDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(nwp + line * 32));
+    }
     if (kind == PH_ATTN) {
       // ---- attention (PO.mm:614-646): this rank's heads, 4 CTAs per head; the result goes to every GPU ----
       if ((int) blockIdx.x < 4 * nh_loc)
-        attention_phase(a, L, sm, rank * nh_loc + (blockIdx.x >> 2), blockIdx.x & 3, pos, a.sp->p_part, o_att + par * E, seq, tid);
+        attention_phase(a, L, sm, rank * nh_loc + (blockIdx.x >> 2), blockIdx.x & 3, pos, a.sp->p_part, o_att + par * E,
+                        ll_me + o_qkv + par * 3u * E, seq, limit, tid);
       PROF_MARK();
       continue;      // no barrier: the consumers poll the flagged words
     }
@@ -798,7 +843,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     if (rp.R == 0) {
       // no rows of this matrix on this CTA (tensor-parallel shards can have fewer row granules than SMs)
       PROF_MARK(); PROF_MARK(); PROF_MARK(); PROF_MARK();
-      if (kind == PH_QKV) { grid_barrier(a.bar, phase, tid, limit); PROF_MARK(); }
+      if (kind == PH_QKV) PROF_MARK();
       continue;
     }
 
@@ -884,12 +929,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           y0 = (float) __dsub_rn(__dmul_rn(x0, cs.x), __dmul_rn(x1, cs.y));
           y1 = (float) __dadd_rn(__dmul_rn(x0, cs.y), __dmul_rn(x1, cs.x));
         }
-        float *dst = which == 0 ? a.q + col : which == 1 ? L.k_layer + (size_t) pos * E + col : L.v_layer + (size_t) pos * E + col;
-        dst[0] = y0;
-        dst[1] = y1;
+        if (which > 0) {                            // the cache row of this position: read by FUTURE tokens (later launches)
+          float *dst = which == 1 ? L.k_layer + (size_t) pos * E + col : L.v_layer + (size_t) pos * E + col;
+          dst[0] = y0;
+          dst[1] = y1;
+        }
+        uint2 *now = ll_me + o_qkv + par * 3u * E + (uint32_t) which * E + col;   // this token's attention reads these
+        ll_store(now, y0, seq);
+        ll_store(now + 1, y1, seq);
       }
       PROF_MARK();
-      grid_barrier(a.bar, phase, tid, limit);     // attention reads plain f32 (q, the K/V cache rows): counter barrier
     } else if (kind == PH_W13) {
       // fused rows 2i = w1 row i, 2i+1 = w3 row i: silu(w1 x) * (w3 x), PO.mm:678-680; silu via the fp16 table (ggml.c:1955-1963)
       for (int i = tid; i < rp.R / 2; i += MEGA_COMPUTE_THREADS) {
