@@ -27,6 +27,9 @@
 #ifndef B200_PLAIN_LOCAL
 #define B200_PLAIN_LOCAL 1  // single GPU: att and h (the mat-vec inputs that need no LayerNorm) cross phases as plain f32 +
 #endif                      // release/acquire arrival counters; measured 1.0 / 2.3 us per layer faster than flagged words
+#ifndef B200_PLAIN_H_GROUP
+#define B200_PLAIN_H_GROUP 0  // tensor-parallel group: h as plain f32 + system-scope release -- measured 3 % SLOWER than flagged words (682 vs 705 tok/s on 2 GPUs)
+#endif
 #ifndef B200_PLAIN_X
 #define B200_PLAIN_X 0      // single GPU: the same for the residual stream (inpL, inpFF); measured 0.5-1.0 us SLOWER
 #endif
@@ -199,11 +202,17 @@ __device__ __forceinline__ int rot_item(int idx, int items, int rot) {
 // values travel as plain f32 (half the L2 read traffic) and the counter that is only a hint for the flagged words
 // becomes the synchronisation: producers' stores -> bar.sync -> red.release.gpu; consumer: ld.acquire.gpu -> bar.sync.
 __device__ __forceinline__ void plain_arrive(unsigned int *cnt) { red_release_add_u32(cnt, 1u); }
-__device__ __forceinline__ void plain_wait(const unsigned int *cnt, unsigned int expected, long long limit, int tid) {
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// sys: the producers are on several GPUs (their stores came over NVLink and were released with a system-scope fence)
+__device__ __forceinline__ void plain_wait(const unsigned int *cnt, unsigned int expected, long long limit, int tid, bool sys = false) {
   if (tid == 0) {
-    if ((int) (ld_acquire_u32(cnt) - expected) < 0) {
+    if ((int) ((sys ? ld_acquire_sys_u32(cnt) : ld_acquire_u32(cnt)) - expected) < 0) {
       const long long t0 = clock64();
-      while ((int) (ld_acquire_u32(cnt) - expected) < 0) {
+      while ((int) ((sys ? ld_acquire_sys_u32(cnt) : ld_acquire_u32(cnt)) - expected) < 0) {
         __nanosleep(20);
         if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
       }
@@ -794,7 +803,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   const unsigned int *const hint_me = a.tp.hint[rank];
   const unsigned int rounds0 = (epoch - 1u) * (unsigned int) a.n_layer;
   // one GPU: plain f32 words in the first half of each region + authoritative counters (see plain_wait)
-  const bool plain = B200_PLAIN_LOCAL && T == 1;     // att, h
+  const bool plain = B200_PLAIN_LOCAL && T == 1;     // att
+  // h is the one vector where halving the consumer-side bytes (44 KB instead of 88 KB per CTA at 7B) also pays inside a
+  // group: plain f32 stored to every GPU, system-scope fence + counter as the release, ld.acquire.sys on the consumer
+  const bool plain_h = B200_PLAIN_LOCAL && (T == 1 || B200_PLAIN_H_GROUP);
   const bool plain_x = B200_PLAIN_X && T == 1;       // inpL, inpFF
   unsigned int *const cnt_me = a.tp.hint[rank];
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
@@ -854,10 +866,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
       PROF_MARK();
       prologue_plain(ll_me + o_att + par * E, plain, E / 32, seq, limit, sm, tid);     // PO.mm:649-651
     } else if (kind == PH_W2) {
-      if (plain) plain_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
+      if (plain_h) plain_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid, T > 1);
       else if (B200_HINTS) hint_wait(hint_me + HINT_H, (rounds0 + il + 1u) * a.tp.p_f, limit, tid);
       PROF_MARK();
-      prologue_plain(ll_me + o_h + par * F, plain, F / 32, seq, limit, sm, tid);       // PO.mm:682-684
+      prologue_plain(ll_me + o_h + par * F, plain_h, F / 32, seq, limit, sm, tid);     // PO.mm:682-684
     } else {
       double xd[MEGA_NORM_ROUNDS][8];
       if (step == 0) {
@@ -947,13 +959,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           const uint16_t hx = __half_as_ushort(__float2half_rn(sm.rowres[2 * i]));
           const float sv = __half2float(__ushort_as_half(__ldg(a.silu_table + hx)));
           const float hv = __fmul_rn(sv, sm.rowres[2 * i + 1]);
-          if (plain) __stcg(reinterpret_cast<float *>(ll_me + o_h + par * F) + g, hv);
-          else ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, hv, seq);
+          if (plain_h) {
+            for (int p = 0; p < T; p++) __stcg(reinterpret_cast<float *>(a.tp.ll[p] + o_h + par * F) + rank * f_loc + g, hv);
+          } else {
+            ll_bcast(a.tp.ll, T, o_h + par * F + rank * f_loc + g, hv, seq);
+          }
         }
       }
-      if (plain) {
+      if (plain_h) {
         named_bar_sync(1, MEGA_COMPUTE_THREADS);
-        if (tid == 0) plain_arrive(cnt_me + HINT_H);
+        if (tid == 0) {
+          if (T == 1) plain_arrive(cnt_me + HINT_H);
+          else { __threadfence_system(); hint_arrive(a.tp.hint, T, HINT_H); }   // fence + relaxed add = release at system scope
+        }
       } else if (B200_HINTS) {
         named_bar_sync(1, MEGA_COMPUTE_THREADS);
         if (tid == 0) hint_arrive(a.tp.hint, T, HINT_H);
