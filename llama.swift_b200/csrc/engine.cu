@@ -256,7 +256,7 @@ struct b200_llama {
   int prof_marks = 0;
   TokenArgs *h_token_args = nullptr;   // host copy of the kernel parameter block (layer descriptors prefilled)
   unsigned int *d_bar = nullptr;
-  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0;
+  int mega_S = 0, mega_stage_bytes = 0, mega_xs_floats = 0, mega_ll_stage = 0;
   size_t mega_smem = 0;
 
   // tensor-parallel group: this handle is rank tp_rank of tp_size; every matrix is split by rows
@@ -326,6 +326,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
+  a.ll_stage = m->mega_ll_stage;
   a.prof = m->d_prof; a.prof_marks = m->prof_marks;
   a.l2_ahead = m->opt_l2_ahead;
   cudaLaunchConfig_t cfg = {};
@@ -778,6 +779,12 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
     m->mega_smem = (size_t) m->mega_S * m->mega_stage_bytes + fixed + (size_t) 2 * m->mega_S * 8;
+    // what is left after the ring (it holds whole stages only) can stage one flagged n_embd-sized vector for the prologues
+    m->mega_ll_stage = 0;
+    if (m->mega_S > 0 && m->mega_smem + 16 + (size_t) E * 8 + 64 <= (size_t) kSmemBudget) {
+      m->mega_ll_stage = 1;
+      m->mega_smem += 16 + (size_t) E * 8 + 64;
+    }
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
     bool fits = rmax_all * 80 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
@@ -1059,7 +1066,7 @@ long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes;
 int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta) {
   if (!m || !mega_usable(m, n_threads) || m->tp_size > 1) return -1;
   cudaSetDevice(m->device);
-  const int marks = 2 + 20 * m->n_layer + 8;
+  const int marks = 2 + 26 * m->n_layer + 12;
   if ((long long) marks * m->n_sm > cap) return -2;
   if (cudaMalloc(&m->d_prof, (size_t) marks * m->n_sm * 8) != cudaSuccess) return -3;
   cudaMemset(m->d_prof, 0, (size_t) marks * m->n_sm * 8);

@@ -30,6 +30,9 @@
 #ifndef B200_PLAIN_H_GROUP
 #define B200_PLAIN_H_GROUP 0  // tensor-parallel group: h as plain f32 + system-scope release -- measured 3 % SLOWER than flagged words (682 vs 705 tok/s on 2 GPUs)
 #endif
+#ifndef B200_LL_STAGE
+#define B200_LL_STAGE 0     // (measured: no gain) flagged n_embd-sized vectors fetched by one TMA bulk copy per CTA, verified from smem
+#endif
 #ifndef B200_PLAIN_X
 #define B200_PLAIN_X 0      // single GPU: the same for the residual stream (inpL, inpFF); measured 0.5-1.0 us SLOWER
 #endif
@@ -99,6 +102,7 @@ struct TokenArgs {
   float kq_scale;
   int S, stage_bytes;
   int xs_floats;            // size of the f32 scratch area (attention scores): >= n_ctx
+  int ll_stage;             // != 0: shared memory has room to stage one n_embd-sized flagged vector (TMA bulk copy)
   int l2_ahead;             // chunks the L2-prefetch warp may run ahead of the loader (0 = off)
   long long *prof;          // optional [gridDim.x][prof_marks] globaltimer stamps (development profiler), else null
   int prof_marks;
@@ -249,6 +253,8 @@ struct MegaSmem {
   double2 *ropev;   // [head_dim/2] (cos, sin) of this token's position, fetched once at kernel start
   float *qkc;       // [288] this token's q (128), k (128) of the head and v (32) of the head quarter, for the attention phase
   uint64_t *full, *empty;
+  uint2 *llbuf;     // [n_embd] staging area for a flagged activation vector (null when it does not fit)
+  uint64_t *llbar;  // its mbarrier
 };
 
 // Block-wide sums over the compute warps with ONE barrier: warp shuffle tree, 14 partials, then every warp folds the
@@ -352,6 +358,43 @@ __device__ __forceinline__ void zero_pad_blocks(int nb, const MegaSmem &sm, int 
   }
 }
 
+// The same from a copy of the whole vector that ONE cp.async.bulk put into shared memory (sm.llbuf): 148 CTAs x 512
+// threads x 4 separate 16-byte requests for the same 32 KB is what made the flagged read slow (L2 request rate); the TMA
+// engine fetches whole lines.  Every word is still verified; a word whose store had not landed when the copy ran is
+// re-polled from global memory.
+template <int N>
+__device__ __forceinline__ void ll_read_rounds_staged(const uint2 *stage, const uint2 *src, int items, uint32_t seq, long long limit,
+                                                      float (&v)[N][8], int tid) {
+#pragma unroll
+  for (int rd = 0; rd < N; rd++) {
+    const int it = min(tid + rd * MEGA_COMPUTE_THREADS, items - 1);
+    const uint4 *ps = reinterpret_cast<const uint4 *>(stage + (size_t) it * 8);
+    const uint4 *pg = reinterpret_cast<const uint4 *>(src + (size_t) it * 8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 r = ps[i];
+      if (r.y != seq || r.w != seq) {
+        const long long t0 = clock64();
+        do {
+          r = ld_vol_v4(pg + i);
+          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+        } while (r.y != seq || r.w != seq);
+      }
+      v[rd][2 * i] = __uint_as_float(r.x);
+      v[rd][2 * i + 1] = __uint_as_float(r.z);
+    }
+  }
+}
+// issue the copy (thread 0) and wait for it (everybody); `par` is the phase parity of sm.llbar, toggled per use
+__device__ __forceinline__ void ll_stage_vector(const MegaSmem &sm, const uint2 *src, int n_words, uint32_t &par, int tid) {
+  if (tid == 0) {
+    mbar_arrive_expect_tx(sm.llbar, (uint32_t) n_words * 8u);
+    tma_bulk_g2s(sm.llbuf, src, (uint32_t) n_words * 8u, sm.llbar);
+  }
+  mbar_wait(sm.llbar, par);
+  par ^= 1u;
+}
+
 // PLAIN: quantize x[K] (flagged words, polled) -> xq/dxs.
 template <int N>
 __device__ __forceinline__ void prologue_plain_batch(const uint2 *src, bool plain, int items, int it0, int rot, uint32_t seq, long long limit,
@@ -387,8 +430,16 @@ __device__ __forceinline__ void prologue_plain(const uint2 *src, bool plain, int
 // NORM: LayerNorm (ggml_compute_forward_norm_f32, ggml.c:5363-5381; double sums, here in tree order) times the norm
 // weight (ggml_mul, PO.mm:573-575), then quantize.  The vector lives in registers as doubles: xd[rd][0..8) is item
 // tid + rd*448 (caller-filled; padding items must be zero-filled and are excluded from the sums by `items`).
+#ifndef B200_PROF_LN
+#define B200_PROF_LN 0      // development: 3 extra timeline marks inside every LayerNorm prologue
+#endif
+#if B200_PROF_LN
+#define LN_MARK() do { if (prof && tid == 0) prof[pm] = globaltimer_ns(); pm++; } while (0)
+#else
+#define LN_MARK() do { } while (0)
+#endif
 __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS][8], const float *norm_w, int nb,
-                                                   const MegaSmem &sm, int tid) {
+                                                   const MegaSmem &sm, int tid, long long *prof, int &pm) {
   const int K = nb * 32, items = nb * 4;
   // the norm weights do not depend on the upstream phase: fetch them now, under the latency of everything below
   float4 wa[MEGA_NORM_ROUNDS], wc[MEGA_NORM_ROUNDS];
@@ -409,6 +460,7 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
     }
   }
   s = mega_sum_d(s, sm.redd, 0, tid);
+  LN_MARK();
   const double mean = pow2 ? __dmul_rn(s, invK) : s / (double) K;
   double s2 = 0.0;
 #pragma unroll
@@ -424,6 +476,10 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
   s2 = mega_sum_d(s2, sm.redd, 1, tid);
   const double var = pow2 ? __dmul_rn(s2, invK) : s2 / (double) K;
   const float nscale = (float) (1.0 / sqrt(__dadd_rn(var, (double) 1e-5f)));               // ggml.c:5379
+#if B200_PROF_LN
+  if (nscale == 123.456f) sm.dxs[0] = nscale;   // keeps the mark below after the division (never true in practice)
+#endif
+  LN_MARK();
 #pragma unroll
   for (int rd = 0; rd < MEGA_NORM_ROUNDS; rd++) {
     if (rd * MEGA_COMPUTE_THREADS < items) {      // CTA-uniform: whole rounds only
@@ -443,10 +499,20 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
 
 // fill the register copy of a flagged activation vector (polled)
 __device__ __forceinline__ void load_items(double (&xd)[MEGA_NORM_ROUNDS][8], const uint2 *src, bool plain, int nb, uint32_t seq,
-                                           long long limit, int tid) {
+                                           long long limit, const MegaSmem &sm, uint32_t &ll_par, int tid) {
   const int items = nb * 4;
   float v[MEGA_NORM_ROUNDS][8];
-  if (plain) {
+  if (!plain && sm.llbuf != nullptr && B200_LL_STAGE) {
+    ll_stage_vector(sm, src, nb * 32, ll_par, tid);
+    if (items <= MEGA_COMPUTE_THREADS) {
+      float v1[1][8];
+      ll_read_rounds_staged<1>(sm.llbuf, src, items, seq, limit, v1, tid);
+#pragma unroll
+      for (int i = 0; i < 8; i++) { v[0][i] = v1[0][i]; v[1][i] = 0.0f; }
+    } else {
+      ll_read_rounds_staged<MEGA_NORM_ROUNDS>(sm.llbuf, src, items, seq, limit, v, tid);
+    }
+  } else if (plain) {
     plain_read_rounds<MEGA_NORM_ROUNDS>(reinterpret_cast<const float *>(src), items, 0, 0, v, tid);
   } else if (items <= MEGA_COMPUTE_THREADS) {
     float v1[1][8];
@@ -698,6 +764,8 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   sm.qkc = reinterpret_cast<float *>(sm.ropev + 64);
   sm.full = reinterpret_cast<uint64_t *>(sm.qkc + 288);
   sm.empty = sm.full + S;
+  sm.llbar = sm.empty + S;
+  sm.llbuf = a.ll_stage ? reinterpret_cast<uint2 *>(sm.llbar + 2) : nullptr;     // 16-byte aligned
   return sm;
 }
 
@@ -713,6 +781,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], MEGA_COMPUTE_WARPS); }
+    mbar_init(sm.llbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -812,6 +881,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   if (tid < HD / 2) sm.ropev[tid] = a.rope[(size_t) pos * (HD / 2) + tid];   // visible after the first prologue's barriers
   RingPos gchunk = {0, 0u, 0u};
   int pm = 0;
+  uint32_t ll_par = 0u;     // phase parity of the staging mbarrier
   PROF_MARK();   // 0: kernel start
   const int n_steps = 5 * a.n_layer + 1;
   for (int step = 0; step < n_steps; step++) {
@@ -856,6 +926,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
       // no rows of this matrix on this CTA (tensor-parallel shards can have fewer row granules than SMs)
       PROF_MARK(); PROF_MARK(); PROF_MARK(); PROF_MARK();
       if (kind == PH_QKV) PROF_MARK();
+#if B200_PROF_LN
+      if (kind == PH_QKV || kind == PH_W13 || kind == PH_OUT) { PROF_MARK(); PROF_MARK(); PROF_MARK(); }
+#endif
       continue;
     }
 
@@ -907,10 +980,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         if (plain_x) plain_wait(cnt, expected, limit, tid);
         else if (B200_HINTS) hint_wait(cnt, expected, limit, tid);
         PROF_MARK();
-        load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, plain_x, E / 32, seq, limit, tid);
+        load_items(xd, ll_me + (kind == PH_W13 ? o_inpFF : o_inpL) + par * E, plain_x, E / 32, seq, limit, sm, ll_par, tid);
       }
       const float *nw = kind == PH_QKV ? L.attn_norm : kind == PH_W13 ? L.ffn_norm : a.final_norm;
-      prologue_norm_regs(xd, nw, E / 32, sm, tid);                              // PO.mm:570-575, 660-665, 694-701
+      prologue_norm_regs(xd, nw, E / 32, sm, tid, a.prof ? a.prof + (size_t) blockIdx.x * a.prof_marks : nullptr, pm);   // PO.mm:570-575, 660-665, 694-701
+#if B200_PROF_LN
+      PROF_MARK();
+#endif
     }
     PROF_MARK();
 

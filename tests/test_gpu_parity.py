@@ -221,3 +221,34 @@ def test_llama_eval_q4_1_vs_oracle(oracle_lib):
     finally:
         ora.free()
         gpu.free()
+
+
+def test_13b_shapes_vs_oracle(oracle_lib):
+    """LLaMA-13B geometry (n_embd 5120, 40 heads, n_ff 13824; BASELINE.json configs[3]) from a TWO-PART model file
+    (LLAMA_N_PARTS, PO.mm:33-38; column/row merge PO.mm:358-388): non-power-of-two LayerNorm length, 4 quantization rounds
+    for the w2 input, 188-row CTAs.  One layer, both schedulers."""
+    path = model_file(n_layer=1, n_vocab=512, seed=31, n_embd=5120)
+    assert os.path.exists(path + ".1"), "expected a two-part model file"
+    ora = CpuModel(oracle_lib, "ora", path, 32)
+    try:
+        for mega in (1, 0):
+            gpu = lsb.llama_model_load(path, n_ctx=32)
+            gpu.set_option("mega", mega)
+            try:
+                assert gpu.n_embd == 5120 and gpu.n_head == 40
+                rng = np.random.default_rng(9)
+                n_past, exact = 0, 0
+                steps = (4, 9, 1, 1, 1)
+                for n in steps:
+                    toks = rng.integers(3, 512, size=n).astype(np.int32)
+                    want = ora.eval(8, n_past, toks)
+                    got = lsb.llama_eval(gpu, 8, n_past, toks)
+                    same, r = _report(f"13B-shape mega={mega} n_past={n_past} N={n}", got, want)
+                    assert r <= 1e-3 and got.argmax() == want.argmax()
+                    exact += same
+                    n_past += n
+                assert exact >= len(steps) - 1
+            finally:
+                gpu.free()
+    finally:
+        ora.free()

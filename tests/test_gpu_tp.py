@@ -55,6 +55,33 @@ def test_tp_group_single_process(oracle_lib, small_model, tp):
         grp.free()
 
 
+@pytest.mark.parametrize("tp", [2, 4, 8])
+def test_tp_group_13b_shapes(oracle_lib, tp):
+    """BASELINE.json configs[3]: LLaMA-13B geometry (two-part file, 40 heads, n_ff 13824) row-sharded over the group."""
+    if _n_gpus() < tp:
+        pytest.skip(f"needs {tp} GPUs")
+    from conftest import model_file
+    path = model_file(n_layer=1, n_vocab=512, seed=31, n_embd=5120)
+    ora = CpuModel(oracle_lib, "ora", path, 32)
+    grp = lsb.llama_model_load_group(path, n_ctx=32, devices=tuple(range(tp)))
+    try:
+        rng = np.random.default_rng(13)
+        n_past, exact = 0, 0
+        steps = (4, 9, 1, 1, 1)
+        for n in steps:
+            toks = rng.integers(3, 512, size=n).astype(np.int32)
+            want = ora.eval(8, n_past, toks)
+            g = lsb.llama_eval(grp, 8, n_past, toks)
+            assert rel_l2(g, want) <= 1e-3 and g.argmax() == want.argmax()
+            exact += int(np.array_equal(bits(g), bits(want)))
+            n_past += n
+        print(f"[tp] 13B shapes over {tp} GPUs: {exact}/{len(steps)} evaluations bit-identical to the oracle")
+        assert exact >= len(steps) - 1
+    finally:
+        ora.free()
+        grp.free()
+
+
 def test_tp_ipc_two_processes(oracle_lib, small_model):
     """One process per GPU (the bench.py / torchrun launch): IPC handles over gloo, lock-step evaluation."""
     if _n_gpus() < 2:

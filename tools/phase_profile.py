@@ -25,7 +25,7 @@ toks, _, ms = m.decode_device(8, 5, args.pos - 8, n_threads=8)     # fill the ca
 print(f"decode {args.pos - 8} steps: {ms / (args.pos - 8) * 1e3:.1f} us/token")
 L = lsb.lib()
 L.b200_llama_profile_token.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
-cap = 148 * (2 + 20 * args.layers + 8) + 1024
+cap = 148 * (2 + 26 * args.layers + 12) + 1024
 buf = np.zeros(cap, dtype=np.int64)
 ncta = C.c_int(0)
 for rep in range(3):
@@ -39,6 +39,11 @@ names = ["qkv wait (arrival)", "qkv read+norm+quant", "qkv rows", "qkv epilogue"
          "wo wait (arrival)", "wo read+quant", "wo rows", "wo epilogue",
          "w13 wait (arrival)", "w13 read+norm+quant", "w13 rows", "w13 epilogue",
          "w2 wait (arrival)", "w2 read+quant", "w2 rows", "w2 epilogue"]
+if os.environ.get("B200_PROF_LN") == "1":     # a -DB200_PROF_LN=1 build: 3 extra marks inside each LayerNorm prologue
+    ln = lambda p: [p + " read+sum1", p + " sum2+rsqrt", p + " mul+quant", p + " (end)"]
+    names = (["qkv wait (arrival)"] + ln("qkv") + ["qkv rows", "qkv epilogue", "barrier (qkv->attn)", "attention",
+             "wo wait (arrival)", "wo read+quant", "wo rows", "wo epilogue", "w13 wait (arrival)"] + ln("w13") +
+             ["w13 rows", "w13 epilogue", "w2 wait (arrival)", "w2 read+quant", "w2 rows", "w2 epilogue"])
 NM = len(names)
 nl = args.layers
 print(f"layers {nl} pos {args.pos}: kernel span {t[:, NM * nl + 4].max():.1f} us; "
