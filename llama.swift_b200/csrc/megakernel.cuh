@@ -891,12 +891,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const uint32_t seq = seq0 + (uint32_t) il;
     const uint32_t par = (uint32_t) il & 1u;
 
-    if (kind == PH_QKV && (int) blockIdx.x < 4 * nh_loc && pos > 0) {
+    for (int unit = blockIdx.x; kind == PH_QKV && pos > 0 && unit < 4 * nh_loc; unit += gridDim.x) {
       // The K/V rows of earlier positions that this CTA's attention phase will read were written many tokens ago and have
       // left L2 (the cache is 1 MB per position at 7B): start pulling them from HBM now, a whole mat-vec phase early.
       // K rows of the head are shared by its 4 CTAs (each takes every 4th position, 4 lines per row); V: this CTA's
       // 32-dim quarter of every row (1 line).
-      const int hh = rank * nh_loc + ((int) blockIdx.x >> 2), qq = (int) blockIdx.x & 3;
+      const int hh = rank * nh_loc + (unit >> 2), qq = unit & 3;
       const float *kb = L.k_layer + hh * HD, *vb = L.v_layer + hh * HD + qq * 32;
       const int nk = ((pos + 3 - qq) >> 2) * 4;          // (positions j = qq, qq+4, ... < pos) x 4 lines
       for (int i = tid; i < nk + pos; i += MEGA_COMPUTE_THREADS) {
@@ -912,9 +912,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         for (int line = blockIdx.x; line * 32 < E; line += gridDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(nwp + line * 32));
     }
     if (kind == PH_ATTN) {
-      // ---- attention (PO.mm:614-646): this rank's heads, 4 CTAs per head; the result goes to every GPU ----
-      if ((int) blockIdx.x < 4 * nh_loc)
-        attention_phase(a, L, sm, rank * nh_loc + (blockIdx.x >> 2), blockIdx.x & 3, pos, a.sp->p_part, o_att + par * E,
+      // ---- attention (PO.mm:614-646): this rank's heads, one (head, 32-dim quarter) unit per CTA -- a second round for
+      // models with more than gridDim/4 heads per GPU (13B: 160 units on 148 CTAs); the result goes to every GPU ----
+      for (int unit = blockIdx.x; unit < 4 * nh_loc; unit += gridDim.x)
+        attention_phase(a, L, sm, rank * nh_loc + (unit >> 2), unit & 3, pos, a.sp->p_part, o_att + par * E,
                         ll_me + o_qkv + par * 3u * E, seq, limit, tid);
       PROF_MARK();
       continue;      // no barrier: the consumers poll the flagged words
