@@ -61,35 +61,65 @@ def ensure_model(layers: int) -> str:
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a query costs
+    ~1 ms, so even a 0.2 s region gets dozens of samples); falls back to polling `nvidia-smi` when pynvml is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    MASKS = [0x8, 0x40, 0x20, 0x4]       # nvmlClocksThrottleReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, "nvml"
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
+
+    def _nvml_sample(self):
+        nv, h = self.nv, self.h
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = 0.0
+        return [sm, self.sm_max, power] + [bool(reasons & m) for m in self.MASKS]
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return None
+        f = [x.strip() for x in out.split(",")]
+        return [float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                smp = self._nvml_sample() if self.nv is not None else self._smi_sample()
+                if smp is not None:
+                    self.samples.append(smp)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.005 if self.nv is not None else 0.05)
 
     def summary(self):
         self.stop_flag = True
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (neither NVML nor nvidia-smi answered)"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[3 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples), "source": self.source}
 
 
 def ref_lib():
