@@ -71,6 +71,9 @@ __host__ __device__ __forceinline__ int cta_of_granule(int g_total, int n_cta, i
 //     float 12582912 + 16*isum, and one fma.rn.f32x2 by (1/16, 1/16) plus (-786432, -786432) yields exact (float) isum.
 __device__ __forceinline__ int lane_elem(int lane, int k) { return (k < 2 ? 0 : 16) + 2 * lane + (k & 1); }
 
+#ifndef B200_LOP3
+#define B200_LOP3 1         // nibble -> signed byte with one LOP3 (see and_xor in ptx.cuh)
+#endif
 #ifndef B200_PIPE
 #define B200_PIPE 1         // small register footprints: two quads in registers, loads of quad q+1 issued under the math of quad q
 #endif
@@ -130,8 +133,13 @@ __device__ __forceinline__ void quad_math(const QuadRegs<LP, RPT> &q, u64 (&acc)
         const uint32_t w = b == 0 ? q.w[i][j].x : b == 1 ? q.w[i][j].y : b == 2 ? q.w[i][j].z : q.w[i][j].w;
         const uint4 xv = q.x[j][b >> 1];
         const int xlo = (int) ((b & 1) ? xv.z : xv.x), xhi = (int) ((b & 1) ? xv.w : xv.y);
+#if B200_LOP3
+        const int a_hi = (int) and_xor(w, 0xF0F0F0F0u, 0x80808080u);             // signed bytes 16*(q-8), lane 2p+1
+        const int a_lo = (int) and_xor(w << 4, 0xF0F0F0F0u, 0x80808080u);        // signed bytes 16*(q-8), lane 2p
+#else
         const int a_hi = (int) ((w & 0xF0F0F0F0u) ^ 0x80808080u);                // signed bytes 16*(q-8), lane 2p+1
         const int a_lo = (int) (((w << 4) & 0xF0F0F0F0u) ^ 0x80808080u);         // signed bytes 16*(q-8), lane 2p
+#endif
         const int ia = dp4a_ss(a_lo, xlo, 0x4B400000);                           // float bits of 12582912 + 16*isum(lane 2p)
         const int ib = dp4a_ss(a_hi, xhi, 0x4B400000);                           // float bits of 12582912 + 16*isum(lane 2p+1)
         const u64 f = ffma2(pack_i2(ia, ib), cvt_mul, cvt_sub);                  // exact (float)isum for both lanes

@@ -31,6 +31,12 @@ __device__ __forceinline__ int dp4a_ss(int a, int b, int c) {
   int d; asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
 
+// (a & b) ^ c in ONE LOP3 (immLut 0x6A).  Written as C++ the compiler splits it into two LOP3s when b and c are both
+// constants (the instruction has a single immediate slot); with register operands one constant stays in a register.
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
