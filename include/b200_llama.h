@@ -75,6 +75,26 @@ int b200_llama_ftype(const b200_llama *m);
 /* gpt_vocab::id_to_token (utils.h:49-55; used at PO.mm:893).  Returns a pointer owned by the model; *len = bytes. */
 const char *b200_llama_token_str(const b200_llama *m, int id, int *len);
 
+/* ---- host-side callees of the token loop -------------------------------------
+ * Same results as the reference's utils.cpp functions, without their O(n_vocab) scans per token; no GPU involved.
+ *
+ * == llama_tokenize(vocab, text, bos), utils.cpp:275-311 (called at PO.mm:810, 815): greedy longest match over the
+ * vocabulary, BOS id 1 first when bos != 0; stops at the first position where no piece matches.  Writes at most `cap`
+ * ids and returns the number of ids the text produces (> cap: buffer too small), or < 0 on bad arguments. */
+typedef struct b200_tokenizer b200_tokenizer;
+b200_tokenizer *b200_tokenizer_create(const b200_llama *m);      /* from the model's vocabulary (gpt_vocab, PO.mm:140-164) */
+b200_tokenizer *b200_tokenizer_create_from(const char *const *pieces, const int *lens, int n_vocab);
+void b200_tokenizer_free(b200_tokenizer *t);
+int b200_llama_tokenize(const b200_tokenizer *t, const char *text, size_t text_len, int bos, int32_t *out, int cap);
+
+/* == llama_sample_top_p_top_k(vocab, logits, last_n_tokens, repeat_penalty, top_k, top_p, temp, rng),
+ * utils.cpp:345-428 (called at PO.mm:865); b200_rng is the std::mt19937 of PO.mm:773.  Returns the sampled id. */
+typedef struct b200_rng b200_rng;
+b200_rng *b200_rng_create(int seed);
+void b200_rng_free(b200_rng *r);
+int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const int32_t *last_n_tokens, int n_last,
+                                      double repeat_penalty, int top_k, double top_p, double temp, b200_rng *rng);
+
 /* Device-resident decode loop (no reference equivalent; used by bench.py's `value` leg and by teacher-forced
  * parity runs).  Starting with `first_token` at position n_past, runs n_steps single-token evaluations entirely on
  * the GPU: after each step the next input token is forced_tokens[i] if forced_tokens != NULL, else the arg-max of

@@ -82,6 +82,15 @@ def lib() -> C.CDLL:
     L.b200_q4_0_matvec.restype = ci
     L.b200_q4_1_matvec.argtypes = [ci, vp, ci, ci, vp, vp, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_1_matvec.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_tokenize"):
+        L.b200_tokenizer_create.argtypes, L.b200_tokenizer_create.restype = [vp], vp
+        L.b200_tokenizer_create_from.argtypes, L.b200_tokenizer_create_from.restype = [C.POINTER(cp), C.POINTER(ci), ci], vp
+        L.b200_tokenizer_free.argtypes, L.b200_tokenizer_free.restype = [vp], None
+        L.b200_llama_tokenize.argtypes, L.b200_llama_tokenize.restype = [vp, cp, sz, ci, vp, ci], ci
+        L.b200_rng_create.argtypes, L.b200_rng_create.restype = [ci], vp
+        L.b200_rng_free.argtypes, L.b200_rng_free.restype = [vp], None
+        L.b200_llama_sample_top_p_top_k.argtypes = [ci, vp, vp, ci, C.c_double, ci, C.c_double, C.c_double, vp]
+        L.b200_llama_sample_top_p_top_k.restype = ci
     _lib = L
     return L
 
@@ -253,3 +262,57 @@ def q4_1_matvec(w_rows: np.ndarray, x: np.ndarray, device: int = 0, timed: bool 
     if rc != 0:
         raise LlamaError(rc, err.value.decode(errors="replace"))
     return (out, ms.value) if timed else out
+
+
+class Tokenizer:
+    """llama_tokenize(vocab, text, bos), utils.cpp:275-311, over a byte trie (include/b200_llama.h)."""
+
+    def __init__(self, model: LlamaModel = None, pieces=None):
+        L = lib()
+        if model is not None:
+            self._h = C.c_void_p(L.b200_tokenizer_create(model._h))
+        else:
+            pieces = [bytes(p) for p in pieces]
+            arr = (C.c_char_p * len(pieces))(*pieces)
+            lens = (C.c_int * len(pieces))(*[len(p) for p in pieces])
+            self._h = C.c_void_p(L.b200_tokenizer_create_from(arr, lens, len(pieces)))
+        if not self._h:
+            raise LlamaError(ERR_LOAD, "tokenizer construction failed")
+
+    def __call__(self, text, bos: bool = True):
+        data = text.encode() if isinstance(text, str) else bytes(text)
+        cap = len(data) + 2
+        out = np.empty(cap, dtype=np.int32)
+        n = lib().b200_llama_tokenize(self._h, data, len(data), int(bos), out.ctypes.data, cap)
+        if n < 0:
+            raise LlamaError(ERR_PREDICT, "tokenize failed")
+        return out[:n].copy()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b200_tokenizer_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Sampler:
+    """llama_sample_top_p_top_k (utils.cpp:345-428) with the std::mt19937 of PO.mm:773; defaults are gpt_params' (utils.h:15-37)."""
+
+    def __init__(self, seed: int = -1):
+        self._h = C.c_void_p(lib().b200_rng_create(seed))
+
+    def sample(self, logits, last_n_tokens, repeat_penalty=1.3, top_k=40, top_p=0.95, temp=0.8) -> int:
+        lg = np.ascontiguousarray(logits, dtype=np.float32)
+        last = np.ascontiguousarray(last_n_tokens, dtype=np.int32)
+        return int(lib().b200_llama_sample_top_p_top_k(len(lg), lg.ctypes.data, last.ctypes.data, len(last),
+                                                       repeat_penalty, top_k, top_p, temp, self._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b200_rng_free(self._h)
+                self._h = None
+        except Exception:
+            pass

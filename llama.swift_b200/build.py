@@ -1,7 +1,8 @@
 """Build the product library llama.swift_b200/libb200llama.so IN-TREE with nvcc for sm_100a.
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.  No torch, no CPU fallback:
-csrc/engine.cu (kernels + C ABI, nvcc) and csrc/host_math.cpp (host libm constants, g++ via nvcc -x c++ passthrough).
+csrc/engine.cu (kernels + C ABI, nvcc), csrc/host_math.cpp (host libm constants) and csrc/host_text.cpp (tokenizer /
+sampler drop-ins), both g++.
 """
 from __future__ import annotations
 
@@ -32,10 +33,14 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB) -
     # host constants: plain g++ semantics (no contraction, F16C for the fp16 conversions)
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mf16c", "-c",
                            os.path.join(HERE, "csrc", "host_math.cpp"), "-o", obj_host])
+    # host-side tokenizer / sampler drop-ins (same libstdc++ / libm calls as the reference's utils.cpp)
+    obj_text = os.path.join(HERE, "csrc", "host_text.o")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c",
+                           os.path.join(HERE, "csrc", "host_text.cpp"), "-o", obj_text])
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false",                       # FMAs only where the reference has them (explicit fmaf / fma.rn.f32x2)
            "-Xcompiler", "-fPIC", "-shared", "-ccbin", "g++",
-           os.path.join(HERE, "csrc", "engine.cu"), obj_host, "-o", out, "-lcudart"] + list(defs)
+           os.path.join(HERE, "csrc", "engine.cu"), obj_host, obj_text, "-o", out, "-lcudart"] + list(defs)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
