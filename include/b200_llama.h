@@ -64,6 +64,14 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
 /* == ggml_free(model.ctx), PO.mm:900 */
 void b200_llama_free(b200_llama *m);
 
+/* Resident models.  The reference re-reads the model file on every run() (PO.mm:790);
+ * b200_llama_acquire returns the model already resident in HBM for the same (file, n_ctx, device) when no other
+ * operation holds it, else loads it (same errors as b200_llama_load); b200_llama_release gives it back without
+ * freeing; b200_llama_cache_clear frees every idle resident model (e.g. when the LlamaRunner goes away). */
+int b200_llama_acquire(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen);
+void b200_llama_release(b200_llama *m);
+void b200_llama_cache_clear(void);
+
 /* llama_hparams fields the caller reads (PO.mm:41-50) */
 int b200_llama_n_vocab(const b200_llama *m);
 int b200_llama_n_ctx(const b200_llama *m);

@@ -82,6 +82,10 @@ def lib() -> C.CDLL:
     L.b200_q4_0_matvec.restype = ci
     L.b200_q4_1_matvec.argtypes = [ci, vp, ci, ci, vp, vp, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_1_matvec.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_acquire"):
+        L.b200_llama_acquire.argtypes, L.b200_llama_acquire.restype = [cp, ci, ci, C.POINTER(vp), cp, sz], ci
+        L.b200_llama_release.argtypes, L.b200_llama_release.restype = [vp], None
+        L.b200_llama_cache_clear.argtypes, L.b200_llama_cache_clear.restype = [], None
     if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_tokenize"):
         L.b200_tokenizer_create.argtypes, L.b200_tokenizer_create.restype = [vp], vp
         L.b200_tokenizer_create_from.argtypes, L.b200_tokenizer_create_from.restype = [C.POINTER(cp), C.POINTER(ci), ci], vp
@@ -108,10 +112,17 @@ class LlamaModel:
         self.n_head = L.b200_llama_n_head(self._h)
         self.ftype = L.b200_llama_ftype(self._h)
 
+    _cached = False
+
     def free(self) -> None:            # ggml_free(model.ctx), PO.mm:900
         if self._h:
-            lib().b200_llama_free(self._h)
+            if self._cached:
+                lib().b200_llama_release(self._h)      # stays resident for the next run
+            else:
+                lib().b200_llama_free(self._h)
             self._h = None
+
+    release = free
 
     def __del__(self):
         try:
@@ -176,6 +187,23 @@ def llama_model_load(fname: str, n_ctx: int = 512, device: int = 0) -> LlamaMode
     if rc != 0:
         raise LlamaError(rc, err.value.decode(errors="replace"))
     return LlamaModel(h.value)
+
+
+def llama_model_acquire(fname: str, n_ctx: int = 512, device: int = 0) -> LlamaModel:
+    """Like llama_model_load, but a model that a previous run released is handed back without touching the file
+    (the reference re-loads on every run(), PO.mm:790).  Give it back with .release()."""
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_acquire(os.fsencode(fname), n_ctx, device, C.byref(h), err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    m = LlamaModel(h.value)
+    m._cached = True
+    return m
+
+
+def llama_model_cache_clear() -> None:
+    lib().b200_llama_cache_clear()
 
 
 def llama_model_load_group(fname: str, n_ctx: int = 512, devices=(0, 1)) -> LlamaModel:

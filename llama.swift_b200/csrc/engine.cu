@@ -7,6 +7,7 @@
 //
 // There is deliberately no CPU fallback: every entry point fails with an error if CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -15,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -271,7 +273,7 @@ struct b200_llama {
   unsigned int *d_epoch = nullptr;
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_l2_ahead = 0, opt_time_kernel = 0;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0;
   double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
   std::vector<cudaEvent_t> kev;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
@@ -328,7 +330,6 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.xs_floats = m->mega_xs_floats;
   a.ll_stage = m->mega_ll_stage;
   a.prof = m->d_prof; a.prof_marks = m->prof_marks;
-  a.l2_ahead = m->opt_l2_ahead;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(m->n_sm);
   cfg.blockDim = dim3(MEGA_THREADS);
@@ -794,7 +795,6 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     if (!fits) m->mega_S = 0;   // falls back to the per-matrix kernels
   }
   m->opt_mega = env_int("B200_MEGA", 1);
-  m->opt_l2_ahead = env_int("B200_L2_AHEAD", 0);
   m->opt_graph = env_int("B200_GRAPH", 1);
   m->opt_pdl = env_int("B200_PDL", 0);
 
@@ -1028,6 +1028,81 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
 
 void b200_llama_free(b200_llama *m) { free_model(m); }
 
+// ---- resident models ----------------------------------------------------------------------
+// The reference reads the model file again on every run() (llama_model_load inside -[LlamaPredictOperation main],
+// PO.mm:790): 4 GB from disk + upload for a 7B model, several seconds against 0.8 s for 512 generated tokens.  A
+// LlamaRunner-lifetime cache keeps the model in HBM between runs: acquire hands out the resident handle for the same
+// (file, n_ctx, device) when no other operation is using it (concurrent operations each get a private model, as they
+// each need their own KV cache), release gives it back without freeing.  The KV cache needs no reset: llama_eval only
+// ever reads rows that the same run has written (positions < n_past).
+namespace {
+struct CacheEntry {
+  std::string path;
+  int n_ctx, device;
+  long long size, mtime_ns;
+  b200_llama *model;
+  bool in_use;
+};
+std::mutex g_cache_mu;
+std::vector<CacheEntry> g_cache;
+
+bool file_identity(const char *path, long long *size, long long *mtime_ns) {
+  struct stat st;
+  if (stat(path, &st) != 0) return false;
+  *size = (long long) st.st_size;
+  *mtime_ns = (long long) st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
+  return true;
+}
+}  // namespace
+
+int b200_llama_acquire(const char *path, int n_ctx, int device, b200_llama **out, char *err, size_t errlen) {
+  if (!out || !path) { set_err(err, errlen, "null argument"); return B200_LLAMA_ERR_LOAD; }
+  *out = nullptr;
+  long long size = 0, mtime = 0;
+  const bool have_id = file_identity(path, &size, &mtime);
+  if (have_id) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (CacheEntry &e : g_cache) {
+      if (!e.in_use && e.path == path && e.n_ctx == n_ctx && e.device == device && e.size == size && e.mtime_ns == mtime) {
+        e.in_use = true;
+        *out = e.model;
+        return B200_LLAMA_OK;
+      }
+    }
+  }
+  b200_llama *m = nullptr;
+  const int rc = b200_llama_load(path, n_ctx, device, &m, err, errlen);     // same errors as an uncached load
+  if (rc != B200_LLAMA_OK) return rc;
+  if (have_id) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_cache.push_back(CacheEntry{path, n_ctx, device, size, mtime, m, true});
+  }
+  *out = m;
+  return B200_LLAMA_OK;
+}
+
+void b200_llama_release(b200_llama *m) {
+  if (!m) return;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (CacheEntry &e : g_cache)
+      if (e.model == m) { e.in_use = false; return; }
+  }
+  free_model(m);      // was never cached (no file identity): behaves like b200_llama_free
+}
+
+void b200_llama_cache_clear(void) {
+  std::vector<b200_llama *> idle;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size();) {
+      if (!g_cache[i].in_use) { idle.push_back(g_cache[i].model); g_cache.erase(g_cache.begin() + (long) i); }
+      else i++;
+    }
+  }
+  for (b200_llama *m : idle) free_model(m);
+}
+
 int b200_llama_n_vocab(const b200_llama *m) { return m->n_vocab; }
 int b200_llama_n_ctx(const b200_llama *m) { return m->n_ctx; }
 int b200_llama_n_embd(const b200_llama *m) { return m->n_embd; }
@@ -1089,7 +1164,6 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
   if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
   if (!strcmp(key, "time_kernel")) { m->opt_time_kernel = value; return 0; }
-  if (!strcmp(key, "l2_ahead")) { m->opt_l2_ahead = value; if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; } return 0; }
   return -1;
 }
 

@@ -103,7 +103,6 @@ struct TokenArgs {
   int S, stage_bytes;
   int xs_floats;            // size of the f32 scratch area (attention scores): >= n_ctx
   int ll_stage;             // != 0: shared memory has room to stage one n_embd-sized flagged vector (TMA bulk copy)
-  int l2_ahead;             // chunks the L2-prefetch warp may run ahead of the loader (0 = off)
   long long *prof;          // optional [gridDim.x][prof_marks] globaltimer stamps (development profiler), else null
   int prof_marks;
 };
@@ -128,10 +127,6 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // ---- flagged activation words ("LL" protocol: value and ready-flag in one 8-byte single-copy-atomic store) -----------
 __device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
   uint4 r;
@@ -787,20 +782,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   __syncthreads();
 
   if (tid >= MEGA_COMPUTE_THREADS) {
-    // ===== TMA loader warp: the whole token's weight stream for this SM, in schedule order (lane 0).  With
-    // l2_ahead > 0 the whole warp also runs a second cursor that many chunks further down the same schedule and pulls
-    // those lines from HBM into L2 with prefetch.global.L2 (LSU path: the TMA unit is already busy with the demand
-    // stream -- cp.async.bulk.prefetch.L2 through it made things slower), so HBM keeps streaming while the ring is full =====
-    const int lane = tid - MEGA_COMPUTE_THREADS;
-    const bool pf_on = a.l2_ahead > 0;
-    if (lane == 0 || pf_on) {
+    // ===== TMA loader warp: the whole token's weight stream for this SM, in schedule order (lane 0).  (An L2 look-ahead
+    // of the stream -- prefetch.global.L2 or cp.async.bulk.prefetch.L2 further down the schedule while the ring is full --
+    // was measured three times in different forms and was slower every time; it is gone.) =====
+    if (tid == MEGA_COMPUTE_THREADS) {
       RingPos g = {0, 0u, 0u};
 #if B200_EVICT_FIRST
       const uint64_t l2pol = l2_policy_evict_first();
 #endif
       const int n_mats = 4 * a.n_layer + 1;
-      int pm_idx = 0, pk = 0;            // prefetch cursor: matrix index in the schedule, chunk within it
-      uint32_t pg = 0;                   // global index of the next chunk to prefetch
       for (int mi = 0; mi < n_mats; mi++) {
         const MatDesc &md = mi < 4 * a.n_layer ? (&a.layers[mi >> 2].qkv)[mi & 3] : a.out;
         const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
@@ -809,40 +799,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
         const int nchunks = (nbq + cq - 1) / cq;
         const uint8_t *wbase = md.w + (size_t) rp.row0 * nbq * 80;
         for (int k = 0; k < nchunks; k++, g.next(S)) {
-          if (lane == 0) {
-            const int s = g.s;
-            // g.par is the parity of the fill about to start; the slot is free once the consumers released the
-            // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
-            mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
-            const int cqk = min(cq, nbq - k * cq);
-            const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
-            mbar_arrive_expect_tx(&sm.full[s], bytes);
+          const int s = g.s;
+          // g.par is the parity of the fill about to start; the slot is free once the consumers released the
+          // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
+          mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
+          const int cqk = min(cq, nbq - k * cq);
+          const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
+          mbar_arrive_expect_tx(&sm.full[s], bytes);
 #if B200_EVICT_FIRST
-            tma_bulk_g2s_hint(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s], l2pol);
+          tma_bulk_g2s_hint(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s], l2pol);
 #else
-            tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s]);
+          tma_bulk_g2s(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s]);
 #endif
-          }
-          if (pf_on) {
-            __syncwarp();
-            // keep chunks (g.g + S, g.g + S + l2_ahead] of the stream on their way into L2
-            const uint32_t lo = g.g + 1u + (uint32_t) S, hi = lo + (uint32_t) a.l2_ahead;
-            while (pm_idx < n_mats && pg < hi) {
-              const MatDesc &pd = pm_idx < 4 * a.n_layer ? (&a.layers[pm_idx >> 2].qkv)[pm_idx & 3] : a.out;
-              const RowPart pr = row_part(pd.g_total, gridDim.x, blockIdx.x);
-              const int pnbq = (pd.nb + 3) >> 2, pcq = pd.cb >> 2;
-              const int pn = pr.R == 0 ? 0 : (pnbq + pcq - 1) / pcq;
-              if (pk >= pn) { pm_idx++; pk = 0; continue; }
-              if (pg >= lo) {
-                const int pc = min(pcq, pnbq - pk * pcq);
-                const uint8_t *pp = pd.w + (size_t) pr.row0 * pnbq * 80 + (size_t) pk * pcq * pr.R * 80;
-                const int pbytes = pc * pr.R * 80;
-                for (int off = lane * 128; off < pbytes; off += 32 * 128)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off));
-              }
-              pk++; pg++;
-            }
-          }
         }
       }
     }

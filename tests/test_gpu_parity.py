@@ -252,3 +252,37 @@ def test_13b_shapes_vs_oracle(oracle_lib):
                 gpu.free()
     finally:
         ora.free()
+
+
+def test_resident_model_cache(small_model):
+    """the reference re-reads the model file on every run() (PO.mm:790); an acquired model that
+    was released is handed back without loading, and a second run over its dirty KV cache gives the same logits."""
+    import time
+    lsb.llama_model_cache_clear()
+    toks = np.array([1, 17, 33, 250, 9], np.int32)
+    t0 = time.perf_counter()
+    a = lsb.llama_model_acquire(small_model, n_ctx=64)
+    t_load = time.perf_counter() - t0
+    first = lsb.llama_eval(a, 8, 0, toks)
+    step = lsb.llama_eval(a, 8, 5, np.array([int(first.argmax())], np.int32))
+    h1 = a._h.value
+    busy = lsb.llama_model_acquire(small_model, n_ctx=64)       # `a` is in use: a concurrent operation gets its own model
+    assert busy._h.value != h1
+    busy.release()
+    a.release()
+    t0 = time.perf_counter()
+    b = lsb.llama_model_acquire(small_model, n_ctx=64)
+    t_again = time.perf_counter() - t0
+    try:
+        assert b._h.value == h1                                    # the resident model, not a fresh load
+        again = lsb.llama_eval(b, 8, 0, toks)
+        assert np.array_equal(bits(again), bits(first))
+        assert np.array_equal(bits(lsb.llama_eval(b, 8, 5, np.array([int(first.argmax())], np.int32))), bits(step))
+        print(f"[cache] first acquire {t_load * 1e3:.0f} ms, re-acquire {t_again * 1e3:.2f} ms")
+        assert t_again < 0.05 * t_load + 0.005
+        c = lsb.llama_model_acquire(small_model, n_ctx=32)         # another n_ctx is another model
+        assert c.n_ctx == 32
+        c.release()
+    finally:
+        b.release()
+        lsb.llama_model_cache_clear()
