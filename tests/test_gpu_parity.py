@@ -286,3 +286,29 @@ def test_resident_model_cache(small_model):
     finally:
         b.release()
         lsb.llama_model_cache_clear()
+
+
+@pytest.mark.parametrize("n_threads", [8, 3])
+def test_long_context_teacher_forced(oracle_lib, small_model, n_threads):
+    """Positions up to 280: several K.Q rounds per warp, V.P chains long enough for every batch size of the chain loop
+    (n_threads 3 -> 94 positions per chain) and the L2 prefetch of earlier KV rows.  Bit-identical at every step."""
+    n_steps = 280
+    ora = CpuModel(oracle_lib, "ora", small_model, 288)
+    gpu = lsb.llama_model_load(small_model, n_ctx=288)
+    try:
+        rng = np.random.default_rng(17)
+        stream = rng.integers(3, 512, size=n_steps + 1).astype(np.int32)
+        toks, logits, _ = gpu.decode_device(0, int(stream[0]), n_steps, n_threads=n_threads, forced_tokens=stream[1:], want_logits=True)
+        exact, worst = 0, 0.0
+        for i in range(n_steps):
+            want = ora.eval(n_threads, i, stream[i:i + 1])
+            worst = max(worst, rel_l2(logits[i], want))
+            assert int(toks[i]) == int(want.argmax()), i
+            exact += int(np.array_equal(bits(logits[i]), bits(want)))
+        print(f"[parity] long context nth={n_threads}: {exact}/{n_steps} steps bit-identical, worst rel_l2 {worst:.3e}")
+        assert worst <= 1e-3 and exact >= n_steps - 2
+        for il in range(2):
+            assert np.array_equal(bits(gpu.kv_export(il, 1, n_steps)), bits(ora.kv(il, 1, n_steps)))
+    finally:
+        ora.free()
+        gpu.free()
