@@ -113,12 +113,15 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
                              float *elapsed_ms, char *err, size_t errlen);
 
 /* Test-only: KV cache rows [0, n_rows) of one layer in the reference layout [n_ctx][n_embd] f32, K already roped
- * (PO.mm:300-301, 586-587, 604-611).  which: 0 = K, 1 = V. */
+ * (PO.mm:300-301, 586-587, 604-611).  which: 0 = K, 1 = V.  On a tensor-parallel handle only the columns of the
+ * rank's own heads are meaningful (a group handle exports rank 0's copy). */
 int b200_llama_kv_export(const b200_llama *m, int layer, int which, int n_rows, float *out);
 int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const float *in);
 
-/* Introspection for bench.py / profiles: number of kernel launches issued by the last eval/decode call, bytes of
- * quantized weights resident, and a knob to toggle CUDA-graph replay + programmatic dependent launch. */
+/* Introspection for bench.py / profiles: number of kernel launches issued by the last eval/decode call (on a group:
+ * per GPU), bytes of quantized weights resident on this handle's GPU, and run-time options: "graph" (CUDA-graph replay),
+ * "mega" (1 = whole-token kernel, 0 = per-matrix kernels; tensor-parallel handles always use the whole-token kernel),
+ * "pdl" (programmatic dependent launch between the per-matrix kernels), "time_kernel". */
 long long b200_llama_last_launches(const b200_llama *m);
 long long b200_llama_weight_bytes(const b200_llama *m);
 /* With option "time_kernel" = 1, b200_llama_decode_device brackets every token-kernel launch with CUDA events on the
