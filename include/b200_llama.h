@@ -103,6 +103,36 @@ void b200_rng_free(b200_rng *r);
 int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const int32_t *last_n_tokens, int n_last,
                                       double repeat_penalty, int top_k, double top_p, double temp, b200_rng *rng);
 
+uint32_t b200_rng_next_u32(b200_rng *r);
+
+/* ---- the token loop itself: -[LlamaPredictOperation main], PO.mm:768-901, as one call ---------------------------------
+ * The compiled-code mirror of the reference's host layer (csrc/host_runner.cpp): model load (resident between runs),
+ * prompt tokenization with BOS, the 4-token probe evaluation, prompt slices of n_batch + 1 tokens, sampling with the
+ * repetition window, and the event stream of _LlamaEvent (headers/LlamaEvent.h:12-28) delivered through a callback:
+ *   kind STARTED_LOADING_MODEL / FINISHED_LOADING_MODEL / STARTED_GENERATING_OUTPUT / COMPLETED: text = NULL
+ *   kind OUTPUT_TOKEN: text/len = the piece (prompt tokens are echoed too, PO.mm:892-895), code = its id
+ *   kind FAILED: text/len = the message, code = LlamaErrorCode (-1000 load, -1001 predict); the call returns that code. */
+enum { B200_EVENT_STARTED_LOADING_MODEL = 0, B200_EVENT_FINISHED_LOADING_MODEL = 1, B200_EVENT_STARTED_GENERATING_OUTPUT = 2,
+       B200_EVENT_OUTPUT_TOKEN = 3, B200_EVENT_COMPLETED = 4, B200_EVENT_FAILED = 5 };
+typedef void (*b200_event_fn)(void *user, int kind, const char *text, int len, int code);
+typedef struct b200_run_params {   /* gpt_params (utils.h:15-37) as _LlamaRunnerBridge fills it (LlamaRunnerBridge.mm:34-43) */
+  int seed, n_threads, n_predict, repeat_last_n, top_k;
+  float top_p, temp, repeat_penalty;
+  int n_batch;
+  int n_ctx;      /* the reference hard-codes 512 (PO.mm:790) */
+  int device;
+} b200_run_params;
+void b200_run_params_default(b200_run_params *p);
+int b200_llama_run(const char *model_path, const char *prompt, size_t prompt_len, const char *antiprompt, size_t antiprompt_len,
+                   const b200_run_params *params, b200_event_fn on_event, void *user);
+/* The loop with an injected evaluator (same contract as b200_llama_eval): what b200_llama_run drives after loading. */
+typedef int (*b200_eval_fn)(void *ctx, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits_out,
+                            char *err, size_t errlen);
+int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ctx, const b200_tokenizer *tok,
+                        const char *const *pieces, const int *piece_lens, const char *prompt, size_t prompt_len,
+                        const char *antiprompt, size_t antiprompt_len, const b200_run_params *params,
+                        b200_event_fn on_event, void *user);
+
 /* Device-resident decode loop (no reference equivalent; used by bench.py's `value` leg and by teacher-forced
  * parity runs).  Starting with `first_token` at position n_past, runs n_steps single-token evaluations entirely on
  * the GPU: after each step the next input token is forced_tokens[i] if forced_tokens != NULL, else the arg-max of

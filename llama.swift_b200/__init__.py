@@ -35,6 +35,19 @@ class LlamaError(RuntimeError):
         self.message = message
 
 
+class RunParams(C.Structure):
+    """b200_run_params: gpt_params (utils.h:15-37) as _LlamaRunnerBridge fills it (LlamaRunnerBridge.mm:34-43)."""
+    _fields_ = [("seed", C.c_int), ("n_threads", C.c_int), ("n_predict", C.c_int), ("repeat_last_n", C.c_int), ("top_k", C.c_int),
+                ("top_p", C.c_float), ("temp", C.c_float), ("repeat_penalty", C.c_float), ("n_batch", C.c_int), ("n_ctx", C.c_int),
+                ("device", C.c_int)]
+
+
+EVENT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_char), C.c_int, C.c_int)
+EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_float),
+                      C.POINTER(C.c_char), C.c_size_t)
+(EVENT_STARTED_LOADING_MODEL, EVENT_FINISHED_LOADING_MODEL, EVENT_STARTED_GENERATING_OUTPUT, EVENT_OUTPUT_TOKEN, EVENT_COMPLETED,
+ EVENT_FAILED) = range(6)
+
 _lib = None
 
 
@@ -95,6 +108,13 @@ def lib() -> C.CDLL:
         L.b200_rng_free.argtypes, L.b200_rng_free.restype = [vp], None
         L.b200_llama_sample_top_p_top_k.argtypes = [ci, vp, vp, ci, C.c_double, ci, C.c_double, C.c_double, vp]
         L.b200_llama_sample_top_p_top_k.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_run"):
+        L.b200_run_params_default.argtypes, L.b200_run_params_default.restype = [C.POINTER(RunParams)], None
+        L.b200_llama_run.argtypes = [cp, cp, sz, cp, sz, C.POINTER(RunParams), EVENT_FN, vp]
+        L.b200_llama_run.restype = ci
+        L.b200_llama_run_loop.argtypes = [EVAL_FN, vp, ci, ci, vp, C.POINTER(cp), C.POINTER(ci), cp, sz, cp, sz,
+                                          C.POINTER(RunParams), EVENT_FN, vp]
+        L.b200_llama_run_loop.restype = ci
     _lib = L
     return L
 
@@ -344,3 +364,40 @@ class Sampler:
                 self._h = None
         except Exception:
             pass
+
+
+def default_run_params(**overrides) -> RunParams:
+    p = RunParams()
+    lib().b200_run_params_default(C.byref(p))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+class LlamaRunner:
+    """Mirror of the Swift LlamaRunner (Sources/llama/LlamaRunner.swift:11-124) over b200_llama_run: run(prompt) drives
+    the reference's whole token loop (PO.mm:768-901) in the library and hands every event to `on_event(kind, text, code)`;
+    returns the list of (id, piece) it emitted (prompt echo included, like the reference)."""
+
+    def __init__(self, model_path: str):
+        self.model_path = model_path
+
+    def run(self, prompt: str, params: RunParams = None, reverse_prompt: str = "", on_event=None):
+        params = params or default_run_params()
+        out, failure = [], []
+
+        def cb(_user, kind, text, n, code):
+            piece = C.string_at(text, n) if text else b""
+            if kind == EVENT_OUTPUT_TOKEN:
+                out.append((code, piece))
+            elif kind == EVENT_FAILED:
+                failure.append((code, piece.decode(errors="replace")))
+            if on_event:
+                on_event(kind, piece, code)
+
+        keep = EVENT_FN(cb)
+        pb, ab = prompt.encode(), reverse_prompt.encode()
+        rc = lib().b200_llama_run(os.fsencode(self.model_path), pb, len(pb), ab, len(ab), C.byref(params), keep, None)
+        if rc != 0:
+            raise LlamaError(*(failure[0] if failure else (rc, "run failed")))
+        return out

@@ -37,10 +37,14 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB) -
     obj_text = os.path.join(HERE, "csrc", "host_text.o")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c",
                            os.path.join(HERE, "csrc", "host_text.cpp"), "-o", obj_text])
+    # the token loop of -[LlamaPredictOperation main] above the C ABI
+    obj_run = os.path.join(HERE, "csrc", "host_runner.o")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c",
+                           os.path.join(HERE, "csrc", "host_runner.cpp"), "-o", obj_run])
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false",                       # FMAs only where the reference has them (explicit fmaf / fma.rn.f32x2)
            "-Xcompiler", "-fPIC", "-shared", "-ccbin", "g++",
-           os.path.join(HERE, "csrc", "engine.cu"), obj_host, obj_text, "-o", out, "-lcudart"] + list(defs)
+           os.path.join(HERE, "csrc", "engine.cu"), obj_host, obj_text, obj_run, "-o", out, "-lcudart"] + list(defs)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

@@ -113,6 +113,8 @@ b200_rng *b200_rng_create(int seed) {
 
 void b200_rng_free(b200_rng *r) { delete r; }
 
+uint32_t b200_rng_next_u32(b200_rng *r) { return (uint32_t) r->engine(); }   // one raw draw (gpt_random_prompt, utils.cpp:103)
+
 int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const int32_t *last_n_tokens, int n_last,
                                       double repeat_penalty, int top_k, double top_p, double temp, b200_rng *rng) {
   if (!logits || !rng || n_vocab <= 0 || top_k <= 0) return -1;
