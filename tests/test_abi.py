@@ -43,3 +43,18 @@ def test_fails_loudly_without_gpu_or_file(tmp_path):
         with pytest.raises(lsb.LlamaError) as ei:
             lsb.llama_model_load(str(tmp_path / "missing.bin"))
         assert ei.value.code == lsb.ERR_LOAD and "no CUDA device" in ei.value.message
+
+
+def test_runner_fails_loudly_without_gpu(tmp_path):
+    """b200_llama_run (the token loop of -main) posts startedLoadingModel, then failedWithError(-1000) when the model cannot
+    be loaded -- on a box without a GPU that is every run: no CPU path exists."""
+    import torch
+    events = []
+    runner = lsb.LlamaRunner(str(tmp_path / "missing.bin"))
+    with pytest.raises(lsb.LlamaError) as ei:
+        runner.run("hello", on_event=lambda kind, piece, code: events.append((kind, code, piece)))
+    assert ei.value.code == lsb.ERR_LOAD
+    assert events[0][0] == lsb.EVENT_STARTED_LOADING_MODEL
+    assert events[-1][0] == lsb.EVENT_FAILED and events[-1][1] == lsb.ERR_LOAD
+    if not torch.cuda.is_available():
+        assert b"no CUDA device" in events[-1][2]
