@@ -121,3 +121,37 @@ def test_sampler_speed_at_llama_vocab(ref_lib):
     dt = (time.perf_counter() - t0) / 20
     print(f"[host] b200_llama_sample_top_p_top_k at n_vocab {n}: {dt * 1e6:.0f} us per token")
     assert dt < 0.05
+
+
+def _tokenize_restated(pieces, text: bytes, bos: bool):
+    """llama_tokenize (utils.cpp:275-311) restated literally: scan the vocabulary in id order at every position."""
+    out = [1] if bos else []
+    pos = 0
+    while True:
+        best_len, best_id = 0, 0
+        for i, p in enumerate(pieces):
+            if len(p) < best_len or len(p) > len(text) - pos:
+                continue
+            if text[pos:pos + len(p)] == p:
+                best_len, best_id = len(p), i
+        if best_len == 0:
+            break
+        out.append(best_id)
+        pos += best_len
+    return out
+
+
+def test_tokenizer_random_vocabularies():
+    """Property test over random small vocabularies (tiny alphabets make prefixes, duplicates and dead ends frequent)."""
+    from hypothesis import given, settings, strategies as st
+
+    piece = st.binary(min_size=0, max_size=5).map(lambda b: bytes(97 + (x % 3) for x in b))     # alphabet {a, b, c}
+    text = st.binary(min_size=0, max_size=40).map(lambda b: bytes(97 + (x % 4) for x in b))      # 'd' is never in a piece
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(piece, min_size=4, max_size=24), text, st.booleans())
+    def check(pieces, t, bos):
+        tok = lsb.Tokenizer(pieces=pieces)
+        assert list(tok(t, bos=bos)) == _tokenize_restated(pieces, t, bos)
+
+    check()
