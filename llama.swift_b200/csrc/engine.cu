@@ -336,7 +336,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   cfg.dynamicSmemBytes = m->mega_smem;
   cfg.stream = m->stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barriers need it
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they wait for each other's activation words
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;

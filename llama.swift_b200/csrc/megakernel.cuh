@@ -5,13 +5,15 @@
 //   * every Q4_0 weight byte of the token (4.13 GB at 7B) is streamed exactly once through a per-CTA ring of
 //     shared-memory stages by cp.async.bulk (1-D TMA).  The loader walks the static schedule
 //     layer0.{wq|wk|wv, wo, w1|w3, w2}, layer1..., output and runs AHEAD of the compute warps across phase boundaries
-//     by up to the ring capacity (~190 KB/SM, ~28 MB chip-wide), so HBM keeps streaming while the compute warps wait
-//     for activations, run a LayerNorm prologue or the attention phase;
+//     by up to the ring capacity (3 x 56 KB per SM, ~25 MB chip-wide), so HBM keeps streaming while the compute warps
+//     wait for activations, run a LayerNorm prologue or the attention phase;
 //   * activations travel as FLAGGED words: every f32 is stored as an 8-byte {value, sequence} pair (one
-//     st.volatile.v2 -- single-copy atomic) and the consumer's prologue polls the words it needs until the sequence
-//     number of (token, layer) shows up.  Data and "ready" signal arrive in ONE store, so four of the five
-//     grid-wide barriers per layer of a conventional schedule disappear (only qkv -> attention keeps a counter
-//     barrier, because attention reads the plain f32 KV cache);
+//     st.volatile.v2 -- single-copy atomic) and the consumer verifies the sequence number of (token, layer) on every
+//     word it uses.  Data and "ready" signal arrive in ONE store, so all five grid-wide barriers per layer of a
+//     conventional schedule disappear (this token's q / K / V reach the attention phase the same way; the f32 KV cache
+//     row is written for future tokens only).  Arrival counters tell a consumer when a read will succeed, so one thread
+//     polls one word; on a single GPU the two big LayerNorm-free vectors (att, h) travel as plain f32 with that
+//     counter as a release/acquire flag instead (half the consumer-side bytes);
 //   * the same stores go to every GPU of a tensor-parallel group through peer-mapped memory (NVLink 5 / NVSwitch):
 //     the all-gather of finished activation slices IS the epilogue -- no NCCL call, no separate collective kernel.
 //
@@ -97,7 +99,7 @@ struct TokenArgs {
   const double2 *rope;
   const uint16_t *silu_table, *exp_table;
   const StepParams *sp;
-  unsigned int *bar;        // [0] grid-barrier counter, [1] end-of-token CTA counter; zeroed before every launch
+  unsigned int *bar;        // [0] unused, [1] end-of-token CTA counter (tensor-parallel groups); zeroed before every launch
   int n_embd, n_head, n_ctx, n_ff, n_threads;
   float kq_scale;
   int S, stage_bytes;
