@@ -44,6 +44,9 @@
 #ifndef B200_ATT_KB
 #define B200_ATT_KB 8       // K.Q: positions per warp batch (12 and 16 measured slower: register pressure)
 #endif
+#ifndef B200_IDLE_PREFETCH
+#define B200_IDLE_PREFETCH 0  // round-2 experiment (see the loader): L2 bulk prefetch of up to this many chunks while the ring is full
+#endif
 #ifndef B200_HINTS
 #define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
 #endif
@@ -784,15 +787,38 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
   __syncthreads();
 
   if (tid >= MEGA_COMPUTE_THREADS) {
-    // ===== TMA loader warp: the whole token's weight stream for this SM, in schedule order (lane 0).  (An L2 look-ahead
-    // of the stream -- prefetch.global.L2 or cp.async.bulk.prefetch.L2 further down the schedule while the ring is full --
-    // was measured three times in different forms and was slower every time; it is gone.) =====
+    // ===== TMA loader warp: the whole token's weight stream for this SM, in schedule order (lane 0).  A CONTINUOUS L2
+    // look-ahead of the stream (prefetch.global.L2 or cp.async.bulk.prefetch.L2 a fixed distance down the schedule) was
+    // measured three times in different forms and was slower every time.  B200_IDLE_PREFETCH (round-2 experiment, off,
+    // not yet measured) prefetches only while the loader would otherwise block on a full ring, i.e. exactly when HBM
+    // idles: one bulk prefetch per chunk, at most B200_IDLE_PREFETCH chunks beyond the ring. =====
     if (tid == MEGA_COMPUTE_THREADS) {
       RingPos g = {0, 0u, 0u};
 #if B200_EVICT_FIRST
       const uint64_t l2pol = l2_policy_evict_first();
 #endif
       const int n_mats = 4 * a.n_layer + 1;
+#if B200_IDLE_PREFETCH
+      // second cursor over the same schedule: (matrix pf_mi, chunk pf_k) is chunk number pf_g of this CTA's stream
+      int pf_mi = 0, pf_k = 0;
+      uint32_t pf_g = 0;
+      auto prefetch_while_blocked = [&](uint32_t cur_g) {
+        const uint32_t lo = cur_g + (uint32_t) S, hi = lo + (uint32_t) B200_IDLE_PREFETCH;   // chunks the ring cannot hold yet
+        while (pf_mi < n_mats && pf_g < hi) {
+          const MatDesc &pd = pf_mi < 4 * a.n_layer ? (&a.layers[pf_mi >> 2].qkv)[pf_mi & 3] : a.out;
+          const RowPart pr = row_part(pd.g_total, gridDim.x, blockIdx.x);
+          const int pnbq = (pd.nb + 3) >> 2, pcq = pd.cb >> 2;
+          const int pn = pr.R == 0 ? 0 : (pnbq + pcq - 1) / pcq;
+          if (pf_k >= pn) { pf_mi++; pf_k = 0; continue; }
+          if (pf_g >= lo) {
+            const int pc = min(pcq, pnbq - pf_k * pcq);
+            const uint8_t *pp = pd.w + (size_t) pr.row0 * pnbq * 80 + (size_t) pf_k * pcq * pr.R * 80;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"((uint32_t) (pc * pr.R * 80)) : "memory");
+          }
+          pf_k++; pf_g++;
+        }
+      };
+#endif
       for (int mi = 0; mi < n_mats; mi++) {
         const MatDesc &md = mi < 4 * a.n_layer ? (&a.layers[mi >> 2].qkv)[mi & 3] : a.out;
         const RowPart rp = row_part(md.g_total, gridDim.x, blockIdx.x);
@@ -804,6 +830,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           const int s = g.s;
           // g.par is the parity of the fill about to start; the slot is free once the consumers released the
           // previous fill (parity par ^ 1).  On a fresh barrier that wait returns at once (first lap).
+#if B200_IDLE_PREFETCH
+          if (!mbar_try_wait(&sm.empty[s], g.par ^ 1u)) prefetch_while_blocked(g.g);
+#endif
           mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
           const int cqk = min(cq, nbq - k * cq);
           const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
