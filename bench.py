@@ -137,9 +137,11 @@ def ref_lib():
     return L
 
 
-def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: int):
+def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: int, keep=None, n_vocab: int = 32000):
     """The reference's own llama_eval on the host: 8-token prompt, then greedy single-token steps.  Returns
-    (tokens/s over the timed decode steps, steps timed, description)."""
+    (tokens/s over the timed decode steps, steps timed, description).  keep: optional dict that receives the run's
+    outputs -- "first" (arg-max after the prompt), "tokens" (arg-max of every step) and "logits" [steps, n_vocab] -- for
+    the parity check against the GPU stream."""
     L = ref_lib()
     if L is None:
         return None, 0, "oracle/_ref/libllama_ref.so not available"
@@ -148,11 +150,12 @@ def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: in
     if not h:
         return None, 0, "reference load failed: " + err.value.decode()
     h = C.c_void_p(h)
-    n_vocab = 32000
     logits = np.empty(n_vocab, np.float32)
     toks = np.array(PROMPT, np.int32)
     L.ref_llama_eval(h, n_threads, 0, toks.ctypes.data, len(toks), logits.ctypes.data, err, 512)   # prompt, untimed
     n_past, cur = len(toks), int(logits.argmax())
+    if keep is not None:
+        keep.update({"first": cur, "tokens": [], "logits": []})
     times = []
     t_begin = time.perf_counter()
     while len(times) < max_steps and n_past < 62:
@@ -162,6 +165,9 @@ def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: in
         times.append(time.perf_counter() - t0)          # the reference's own t_predict_us window (PO.mm:837-845)
         n_past += 1
         cur = int(logits.argmax())
+        if keep is not None:
+            keep["tokens"].append(cur)
+            keep["logits"].append(logits.copy())
         if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
             break
     L.ref_llama_free(h)
@@ -169,6 +175,55 @@ def time_reference_cpu(path: str, n_threads: int, budget_s: float, max_steps: in
     med = sorted(times)[len(times) // 2]
     return len(times) / total, len(times), (f"reference ggml CPU path (oracle/_ref, AVX2 build), {n_threads} threads, 8-token prompt then "
                                              f"{len(times)} greedy decode steps at n_past 8..{n_past - 1}; median {med * 1e3:.1f} ms/token")
+
+
+def calibrated_reference_cpu(path: str, budget_s: float, max_steps: int):
+    """The reference CPU arm with "all the host threads it can use": its spin-wait pool (ggml.c:9061-9107, re-created on
+    every llama_eval) gets SLOWER past a point, so every candidate thread count is tried on 3 steps and the fastest one is
+    timed.  Used by BOTH the cpu_baseline leg and --impl reference, so the two report the same thread count."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= cores} | {min(cores, 8)})
+    cal = {}
+    for c in cands:
+        r, _, _ = time_reference_cpu(path, c, budget_s=20.0, max_steps=3)
+        if r is not None:
+            cal[c] = r
+    nth = max(cal, key=cal.get) if cal else min(cores, 8)
+    tps, n, desc = time_reference_cpu(path, nth, budget_s=budget_s, max_steps=max_steps)
+    if tps is not None:
+        desc += ("; thread-count calibration tok/s: " + ", ".join(f"{c}: {v:.2f}" for c, v in sorted(cal.items())) +
+                 f" of {cores} host cores (8 = the Swift default, LlamaRunner.swift:17)")
+    return tps, n, desc, nth, cores
+
+
+PARITY_STEPS = 24
+
+
+def parity_reference(path: str, n_threads: int, n_vocab: int):
+    """Rank 0: PARITY_STEPS greedy steps of the UNMODIFIED reference (oracle/_ref) after the 8-token prompt, with the thread
+    count the GPU run mirrors (the reference's V*P summation order depends on it).  Returns the kept outputs or None."""
+    keep = {}
+    tps, n, _ = time_reference_cpu(path, n_threads, budget_s=120.0, max_steps=PARITY_STEPS, keep=keep, n_vocab=n_vocab)
+    if tps is None or n < 1:
+        return None
+    return keep
+
+
+def parity_block(model, lsb, ref, n_threads: int):
+    """The GPU stream over the same steps, teacher-forced with the reference's tokens so that one flipped arg-max cannot
+    hide the steps after it; every rank of a group makes the same calls, rank 0 compares."""
+    toks = np.array(ref["tokens"], np.int32)
+    n = len(toks)
+    got_first = int(lsb.llama_eval(model, n_threads, 0, np.array(PROMPT, np.int32)).argmax())
+    forced = toks                                            # token fed at step i+1 = the reference's arg-max of step i
+    gtoks, glogits, _ = model.decode_device(N_PROMPT, ref["first"], n, n_threads=n_threads, forced_tokens=forced, want_logits=True)
+    want = np.stack(ref["logits"]).astype(np.float64)
+    got = glogits.astype(np.float64)
+    rel = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
+    bit = int(sum(np.array_equal(glogits[i].view(np.uint32), ref["logits"][i].view(np.uint32)) for i in range(n)))
+    return {"steps": n, "positions": [N_PROMPT, N_PROMPT + n - 1], "vs": "oracle/_ref (unmodified reference llama_eval), %d threads" % n_threads,
+            "argmax_equal": bool(got_first == ref["first"] and np.array_equal(gtoks, toks)), "max_rel_l2": float(rel.max()),
+            "bit_identical_steps": bit, "tolerance": 1e-3, "ok": bool(got_first == ref["first"] and np.array_equal(gtoks, toks) and rel.max() <= 1e-3)}
 
 
 def main():
@@ -180,6 +235,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32, help="debug: fewer layers (the result is then NOT the benchmark)")
     ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 24-step comparison with the reference CPU path")
     ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
                     help="N > 1: tp = ONE bs=1 generation over all GPUs (rows of every matrix split over the ranks; the metric "
                          "BASELINE.json names); replicas = N independent generations")
@@ -191,9 +247,10 @@ def main():
     n_gpus = args.gpus
     steps, warmup = args.steps, max(3, args.warmup)
 
-    config = {"workload": "LLaMA-7B Q4_0 bs=1 decode, 512-token gen after an 8-token prompt (BASELINE.json configs[1])",
+    config = {"workload": "LLaMA-7B Q4_0 bs=1 decode, %d-token gen after an 8-token prompt%s" %
+                          (steps, " (BASELINE.json configs[1])" if steps == 512 else " (BASELINE.json configs[1] is the same with 512 tokens)"),
               "model_file": "synthetic ggml-format 7B (n_embd 4096, n_layer %d, n_vocab 32000), seed 0" % args.layers,
-              "n_past_start": N_PROMPT, "ref_threads_mirrored": args.threads,
+              "n_past_start": N_PROMPT, "positions": [N_PROMPT, N_PROMPT + steps - 1], "ref_threads_mirrored": args.threads,
               "l2_policy": "per-step working set (4.13 GB weights) >> 126 MB L2, no flush needed"}
     if args.layers != 32:
         config["workload"] += f" [DEBUG: {args.layers} layers -- not the benchmark]"
@@ -202,25 +259,13 @@ def main():
         if rank != 0:
             return 0
         path = ensure_model(args.layers)
-        cores = os.cpu_count() or 1
-        # "all the host threads it can use": the reference's spin-wait pool (ggml.c:9061-9107, re-created on every
-        # llama_eval) gets SLOWER past a point, so calibrate on 3 steps each and time the fastest setting
-        cands = sorted({c for c in (8, 16, 32, 64) if c <= cores} | {min(cores, 8)})
-        cal = {}
-        for c in cands:
-            r, _, _ = time_reference_cpu(path, c, budget_s=20.0, max_steps=3)
-            if r is not None:
-                cal[c] = r
-        nth = max(cal, key=cal.get) if cal else min(cores, 8)
-        tps, n, desc = time_reference_cpu(path, nth, budget_s=120.0, max_steps=max(3, min(steps, 54)))
-        if tps is not None:
-            desc += "; thread-count calibration tok/s: " + ", ".join(f"{c}: {v:.2f}" for c, v in sorted(cal.items())) + f" of {cores} host cores"
+        tps, n, desc, nth, cores = calibrated_reference_cpu(path, budget_s=120.0, max_steps=max(3, min(steps, 54)))
         if tps is None:
             print(json.dumps({"impl": "reference", "unavailable": desc}))
             return 0
         line = {"impl": "reference", "metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s",
                 "n_gpus": n_gpus, "steps": n, "warmup": 1, "ms_per_step": 1e3 / tps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int4 x int4 -> int32 block dots, fp32 accumulate (AVX2 CPU)",
+                "scaling": "strong", "vs_baseline": None, "dtype": "int4 x int4 -> int32 block dots, fp32 accumulate (AVX2 CPU)",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": nth, "kind": "reference", "sample": desc},
                 "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -269,6 +314,20 @@ def main():
 
     def prompt():
         return lsb.llama_eval(model, args.threads, 0, np.array(PROMPT, np.int32))
+
+    # ---- parity at the benched configuration: the first PARITY_STEPS steps against the unmodified reference (rank 0 runs
+    # the CPU side and shares its tokens; every rank of a group then makes the same GPU calls) ----
+    parity = None
+    if not args.no_parity:
+        ref = parity_reference(path, args.threads, n_vocab) if rank == 0 else None
+        if dist is not None:
+            box = [ref]
+            dist.broadcast_object_list(box, src=0)
+            ref = box[0]
+        if ref is not None:
+            parity = parity_block(model, lsb, ref, args.threads)
+        elif rank == 0:
+            parity = {"steps": 0, "ok": False, "note": "oracle/_ref/libllama_ref.so not available on this box"}
 
     # ---- warm-up (untimed): prompt + W decode steps, then rewind to the end of the prompt ----
     first = int(prompt().argmax())
@@ -324,24 +383,28 @@ def main():
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tf):
-        traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+    # DRAM bytes per launch come from an `ncu --set full` capture of this kernel on this workload (1 GPU, 32 layers); there is
+    # no capture of a tensor-parallel shard (ncu must not wrap a multi-rank run), so N > 1 reports null
+    traffic, traffic_src = None, None
+    for tf in ("r2_traffic.json", "r1_traffic.json"):
+        tfp = os.path.join(ROOT, "profiles", tf)
+        if world == 1 and args.layers == 32 and os.path.exists(tfp):
+            traffic, traffic_src = json.load(open(tfp)).get("dram_bytes_per_launch"), "profiles/" + tf
+            break
     roofline = None
     if mean_bytes is not None and kernel_ms:
         achieved = mean_bytes / (kernel_ms / steps * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "decode_token_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": mean_bytes, "weights_only_GBps": W_BYTES / (kernel_ms / steps * 1e-3) / 1e9,
                     "kernel_us_per_launch": kernel_ms / steps * 1e3}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        ctps, n, desc = time_reference_cpu(path, 8, budget_s=25.0, max_steps=24)
+        ctps, n, desc, nth, cores = calibrated_reference_cpu(path, budget_s=25.0, max_steps=24)
         if ctps is not None:
-            cpu = {"value": ctps, "unit": "tokens/s", "cores": 8, "kind": "reference", "sample": desc,
-                   "host_cores_available": os.cpu_count()}
+            cpu = {"value": ctps, "unit": "tokens/s", "cores": nth, "kind": "reference", "sample": desc,
+                   "host_cores_available": cores}
         else:
             cpu = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": desc}
 
@@ -357,12 +420,12 @@ def main():
                    "graph": "CUDA graph replay of [memset, decode_token_kernel] + argmax kernel per step"})
     line = {"metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_value / steps, "higher_is_better": True,
-            "scaling": "strong" if tp else "weak", "vs_baseline": None,
+            "scaling": "weak" if (world > 1 and not tp) else "strong", "vs_baseline": None,
             "dtype": "int4 x int4 -> int32 block dots (dp4a), fp32 lane accumulation (bit-exact AVX2 order), f32 KV",
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": jobs * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
                     "note": "b200_llama_eval per token: token id by value, logits to pinned host memory, host arg-max"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line))
     model.free()
     if dist is not None:

@@ -111,6 +111,19 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   }
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
+#if B200_IMMA
+  // Tensor-path row loop (rowloop_imma.cuh): lp = rows per warp tile (8 for few-row matrices, so that 4+ warps share the
+  // work; else 16), rpt = tiles per warp (2 when a CTA owns more than 16 tiles).  lp_override 8 / 16 forces the tile.
+  {
+    int rw = p.rmax <= 64 ? 8 : 16;
+    if (lp_override == 8 || lp_override == 16) rw = lp_override;
+    if ((p.rmax + rw - 1) / rw > MEGA_COMPUTE_WARPS) rw = 16;
+    const int tiles = (p.rmax + rw - 1) / rw;
+    p.lp = rw;
+    p.rpt = tiles > MEGA_COMPUTE_WARPS ? 2 : 1;
+    p.threads = MEGA_COMPUTE_THREADS + 32;
+  }
+#endif
   // One ring stage holds one chunk of whole quads (4 blocks x rmax rows x 80 B) in both the per-matrix kernels and the
   // whole-token kernel; an even number of quads per chunk where possible (the LP = 1 row loop works on quad pairs).
   const int nbq = (p.nb + 3) / 4;
@@ -119,7 +132,11 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   p.cb = cq * 4;
   p.stage_bytes = (cq * p.rmax * 80 + 127) & ~127;
   const int nchunks = (nbq + cq - 1) / cq;
+#if B200_IMMA
+  const size_t fixed = act_smem_bytes(nbq * 4) + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+#else
   const size_t fixed = (size_t) nbq * 4 * 64 + (size_t) nbq * 4 * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+#endif
   int S = (int) ((kSmemBudget - (long) fixed - 256) / (p.stage_bytes + 16));
   S = std::max(1, std::min(S, nchunks));
   p.S = S;
@@ -146,11 +163,18 @@ cudaError_t launch_gemv_t(const GemvPlan &p, const GemvArgs &a, cudaStream_t st,
 
 template <int PRO, int EPI>
 cudaError_t launch_gemv_lp(const GemvPlan &p, const GemvArgs &a, cudaStream_t st, bool pdl) {
+#if B200_IMMA
+  // template slot: 1 = 8-row warp tiles, 2 = 16-row tiles, 4 = two 16-row tiles per warp
+  if (p.lp == 8) return launch_gemv_t<1, PRO, EPI>(p, a, st, pdl);
+  if (p.rpt == 1) return launch_gemv_t<2, PRO, EPI>(p, a, st, pdl);
+  return launch_gemv_t<4, PRO, EPI>(p, a, st, pdl);
+#else
   switch (p.lp) {
     case 1: return launch_gemv_t<1, PRO, EPI>(p, a, st, pdl);
     case 2: return launch_gemv_t<2, PRO, EPI>(p, a, st, pdl);
     default: return launch_gemv_t<4, PRO, EPI>(p, a, st, pdl);
   }
+#endif
 }
 
 template <int PRO, int EPI>
@@ -459,7 +483,7 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice
   } else {
     const long long total = (long long) p.g_total * 4 * ((p.nb + 3) / 4) * 4;
     repack_q4_0_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(
-        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half, p.lp);
+        d_stage, p.d_w, p.M, p.g_total, p.nb, p.cb, p.n_cta, interleave_half, B200_IMMA ? 0 : p.lp);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -775,7 +799,8 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     const int nb_max = ((std::max(E, F) / 32) + 3) & ~3;     // whole quads
     m->mega_xs_floats = (n_ctx + 3) & ~3;
     m->mega_stage_bytes = stage_bytes_cfg();
-    const size_t fixed = (size_t) (nb_max + 2) * 32 + (size_t) ((nb_max + 3) & ~3) * 4 + (size_t) m->mega_xs_floats * 4 +
+    const size_t act_bytes = B200_IMMA ? act_smem_bytes(nb_max) : (size_t) (nb_max + 2) * 32 + (size_t) ((nb_max + 3) & ~3) * 4;
+    const size_t fixed = act_bytes + (size_t) m->mega_xs_floats * 4 +
                          MEGA_MAX_ROWS * 4 + 32 * 8 + 32 * 4 + MEGA_MAX_NTH * 32 * 4 + 64 * 16 + 288 * 4 + MEGA_COMPUTE_WARPS * 4;
     const long ring = (long) kSmemBudget - (long) fixed - 256;
     m->mega_S = ring > 0 ? (int) (ring / (m->mega_stage_bytes + 16)) : 0;
@@ -789,7 +814,11 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     int rmax_all = m->out.rmax;
     for (auto &L : m->layers) rmax_all = std::max({rmax_all, L.qkv.rmax, L.wo.rmax, L.w13.rmax, L.w2.rmax});
     bool fits = rmax_all * 80 <= m->mega_stage_bytes && E / 8 <= MEGA_NORM_ROUNDS * MEGA_COMPUTE_THREADS && m->n_layer <= MEGA_MAX_LAYERS && F / 8 <= 6 * MEGA_COMPUTE_THREADS;
+#if B200_IMMA
+    auto rows_fit = [&](const GemvPlan &p) { return (p.rmax + p.lp - 1) / p.lp <= MEGA_COMPUTE_WARPS * p.rpt && p.rmax <= MEGA_MAX_ROWS; };
+#else
     auto rows_fit = [&](const GemvPlan &p) { return p.rmax / p.rpt * (4 / p.lp) <= MEGA_COMPUTE_THREADS && p.rmax <= MEGA_MAX_ROWS; };
+#endif
     fits = fits && rows_fit(m->out);
     for (auto &L : m->layers) fits = fits && rows_fit(L.qkv) && rows_fit(L.wo) && rows_fit(L.w13) && rows_fit(L.w2);
     if (!fits) m->mega_S = 0;   // falls back to the per-matrix kernels
@@ -893,19 +922,16 @@ static std::vector<b200_llama *> ranks_of(b200_llama *m) {
   return m->group.empty() ? std::vector<b200_llama *>{m} : m->group;
 }
 
-static int eval_enqueue(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, char *err, size_t errlen) {
+// One token of a batch on one rank.  The reference evaluates the N columns of every mat-mul independently, so a batch is
+// run one token at a time; p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P
+// partition, ggml.c:5628).
+static int eval_enqueue_token(b200_llama *m, int n_threads, int token, int pos, int p_part, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
-  m->last_launches = 0;
-  // The reference evaluates the N columns of every mat-mul independently, so the batch is run one token at a time;
-  // p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P partition, ggml.c:5628).
-  for (int i = 0; i < n_tokens; i++) {
-    set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, tokens[i], n_past + i, n_past + n_tokens, 0);
-    CUDA_TRY(cudaGetLastError());
-    m->last_launches++;
-    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
-  }
-  CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, p_part, 0);
+  CUDA_TRY(cudaGetLastError());
+  m->last_launches++;
+  CUDA_TRY(run_token(m, n_threads, &m->last_launches));
   return B200_LLAMA_OK;
 }
 
@@ -924,9 +950,22 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
   }
   if (const char *why = tp_ready(m, n_threads)) { set_err(err, errlen, "%s", why); return fail_code; }
   const std::vector<b200_llama *> ranks = ranks_of(m);
+  for (b200_llama *r : ranks) r->last_launches = 0;
+  // Token-major enqueue: the token kernels of a group wait for each other ON THE GPUS, so every rank must receive
+  // token i before any rank receives so much work that the driver's launch queue blocks the host (one host thread
+  // drives all ranks of a single-process group).
+  for (int i = 0; i < n_tokens; i++) {
+    for (b200_llama *r : ranks) {
+      const int rc = eval_enqueue_token(r, n_threads, tokens[i], n_past + i, n_past + n_tokens, err, errlen);
+      if (rc != B200_LLAMA_OK) return rc;
+    }
+    if (ranks.size() > 1 && (i & 63) == 63) {      // bound the work in flight per rank
+      for (b200_llama *r : ranks) { CUDA_TRY(cudaSetDevice(r->device)); CUDA_TRY(cudaStreamSynchronize(r->stream)); }
+    }
+  }
   for (b200_llama *r : ranks) {
-    const int rc = eval_enqueue(r, n_threads, n_past, tokens, n_tokens, err, errlen);
-    if (rc != B200_LLAMA_OK) return rc;
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaMemcpyAsync(r->h_logits, r->d_logits, (size_t) r->n_vocab * 4, cudaMemcpyDeviceToHost, r->stream));
   }
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
@@ -961,26 +1000,28 @@ static int decode_prepare(b200_llama *m, int n_steps, const int32_t *forced_toke
   return B200_LLAMA_OK;
 }
 
-static int decode_enqueue(b200_llama *m, int n_threads, int n_past, int first_token, int n_steps, bool forced, bool want_logits,
-                          char *err, size_t errlen) {
+static int decode_begin(b200_llama *m, int n_past, int first_token, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
   m->last_launches = 0;
   set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
-  for (int i = 0; i < n_steps; i++) {
-    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
-    CUDA_TRY(run_token(m, n_threads, &m->last_launches));
-    if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
-    if (want_logits) {
-      CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
-    }
-    argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced ? m->d_forced : nullptr);
-    CUDA_TRY(cudaGetLastError());
-    m->last_launches++;
+  return B200_LLAMA_OK;
+}
+
+static int decode_step(b200_llama *m, int n_threads, int i, bool forced, bool want_logits, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
+  CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+  if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
+  if (want_logits) {
+    CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
   }
-  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
+  argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced ? m->d_forced : nullptr);
+  CUDA_TRY(cudaGetLastError());
+  m->last_launches++;
   return B200_LLAMA_OK;
 }
 
@@ -1008,8 +1049,23 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
     if (rc != B200_LLAMA_OK) return rc;
   }
   for (b200_llama *r : ranks) {
-    const int rc = decode_enqueue(r, n_threads, n_past, first_token, n_steps, forced_tokens != nullptr, r == m && logits_all != nullptr, err, errlen);
+    const int rc = decode_begin(r, n_past, first_token, err, errlen);
     if (rc != B200_LLAMA_OK) return rc;
+  }
+  // step-major enqueue (see b200_llama_eval): rank 0's step i must not be queued behind hundreds of its own later steps
+  // while rank 1 has not been given step i yet
+  for (int i = 0; i < n_steps; i++) {
+    for (b200_llama *r : ranks) {
+      const int rc = decode_step(r, n_threads, i, forced_tokens != nullptr, r == m && logits_all != nullptr, err, errlen);
+      if (rc != B200_LLAMA_OK) return rc;
+    }
+    if (ranks.size() > 1 && (i & 63) == 63) {
+      for (b200_llama *r : ranks) { CUDA_TRY(cudaSetDevice(r->device)); CUDA_TRY(cudaStreamSynchronize(r->stream)); }
+    }
+  }
+  for (b200_llama *r : ranks) {
+    CUDA_TRY(cudaSetDevice(r->device));
+    CUDA_TRY(cudaEventRecord(r->ev1, r->stream));
   }
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
@@ -1026,7 +1082,7 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
   return B200_LLAMA_OK;
 }
 
-void b200_llama_free(b200_llama *m) { free_model(m); }
+void b200_llama_free(b200_llama *m);
 
 // ---- resident models ----------------------------------------------------------------------
 // The reference reads the model file again on every run() (llama_model_load inside -[LlamaPredictOperation main],
@@ -1060,6 +1116,7 @@ int b200_llama_acquire(const char *path, int n_ctx, int device, b200_llama **out
   *out = nullptr;
   long long size = 0, mtime = 0;
   const bool have_id = file_identity(path, &size, &mtime);
+  std::vector<b200_llama *> stale;
   if (have_id) {
     std::lock_guard<std::mutex> lock(g_cache_mu);
     for (CacheEntry &e : g_cache) {
@@ -1069,7 +1126,14 @@ int b200_llama_acquire(const char *path, int n_ctx, int device, b200_llama **out
         return B200_LLAMA_OK;
       }
     }
+    // the file was rewritten since an idle entry of the same path was loaded: that entry can never match again
+    for (size_t i = 0; i < g_cache.size();) {
+      CacheEntry &e = g_cache[i];
+      if (!e.in_use && e.path == path && (e.size != size || e.mtime_ns != mtime)) { stale.push_back(e.model); g_cache.erase(g_cache.begin() + (long) i); }
+      else i++;
+    }
   }
+  for (b200_llama *old_model : stale) free_model(old_model);
   b200_llama *m = nullptr;
   const int rc = b200_llama_load(path, n_ctx, device, &m, err, errlen);     // same errors as an uncached load
   if (rc != B200_LLAMA_OK) return rc;
@@ -1083,12 +1147,36 @@ int b200_llama_acquire(const char *path, int n_ctx, int device, b200_llama **out
 
 void b200_llama_release(b200_llama *m) {
   if (!m) return;
+  // a model whose last run failed on the device (a trapped kernel poisons the context) must not be handed out again
+  bool healthy = cudaSetDevice(m->device) == cudaSuccess;
+  if (healthy) {
+    const cudaError_t q = cudaStreamQuery(m->stream);
+    healthy = q == cudaSuccess || q == cudaErrorNotReady;
+  }
   {
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    for (CacheEntry &e : g_cache)
-      if (e.model == m) { e.in_use = false; return; }
+    size_t n_idle_same = 0;
+    for (size_t i = 0; i < g_cache.size(); i++) {
+      if (g_cache[i].model != m) continue;
+      for (const CacheEntry &o : g_cache)
+        if (!o.in_use && o.path == g_cache[i].path && o.n_ctx == g_cache[i].n_ctx && o.device == g_cache[i].device) n_idle_same++;
+      // keep at most one idle copy per (file, n_ctx, device): the private models of concurrent runs are freed on release
+      if (healthy && n_idle_same == 0) { g_cache[i].in_use = false; return; }
+      g_cache.erase(g_cache.begin() + (long) i);
+      break;
+    }
   }
-  free_model(m);      // was never cached (no file identity): behaves like b200_llama_free
+  free_model(m);      // never cached (no file identity), unhealthy, or a surplus copy: behaves like b200_llama_free
+}
+
+void b200_llama_free(b200_llama *m) {
+  if (!m) return;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);      // a handle obtained with acquire may be freed directly: forget it
+    for (size_t i = 0; i < g_cache.size(); i++)
+      if (g_cache[i].model == m) { g_cache.erase(g_cache.begin() + (long) i); break; }
+  }
+  free_model(m);
 }
 
 void b200_llama_cache_clear(void) {
@@ -1118,17 +1206,17 @@ const char *b200_llama_token_str(const b200_llama *m, int id, int *len) {
 
 int b200_llama_kv_export(const b200_llama *m, int layer, int which, int n_rows, float *out) {
   if (!m || layer < 0 || layer >= m->n_layer || n_rows < 0 || n_rows > m->n_ctx) return B200_LLAMA_ERR_PREDICT;
-  cudaSetDevice(m->device);
+  if (cudaSetDevice(m->device) != cudaSuccess) return B200_LLAMA_ERR_PREDICT;
   const float *base = (which == 0 ? m->d_k : m->d_v) + (size_t) layer * m->n_ctx * m->n_embd;
-  cudaStreamSynchronize(m->stream);
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess) return B200_LLAMA_ERR_PREDICT;
   return cudaMemcpy(out, base, (size_t) n_rows * m->n_embd * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200_LLAMA_ERR_PREDICT;
 }
 
 int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const float *in) {
   if (!m || layer < 0 || layer >= m->n_layer || n_rows < 0 || n_rows > m->n_ctx) return B200_LLAMA_ERR_PREDICT;
-  cudaSetDevice(m->device);
+  if (cudaSetDevice(m->device) != cudaSuccess) return B200_LLAMA_ERR_PREDICT;
   float *base = (which == 0 ? m->d_k : m->d_v) + (size_t) layer * m->n_ctx * m->n_embd;
-  cudaStreamSynchronize(m->stream);
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess) return B200_LLAMA_ERR_PREDICT;
   return cudaMemcpy(base, in, (size_t) n_rows * m->n_embd * 4, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : B200_LLAMA_ERR_PREDICT;
 }
 

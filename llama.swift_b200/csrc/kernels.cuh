@@ -20,6 +20,11 @@
 
 #include "ptx.cuh"
 
+#ifndef B200_IMMA
+#define B200_IMMA 0         // 1 = row loops on the warp-level tensor path (rowloop_imma.cuh): EXPERIMENT, measured slower
+#endif
+#include "rowloop_imma.cuh"
+
 namespace b200 {
 
 namespace cg = cooperative_groups;
@@ -322,10 +327,15 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
 
   // shared memory carve-up
   uint8_t *stages = smem;
+#if B200_IMMA
+  const ActSmem act = act_carve(smem + (size_t) S * a.stage_bytes, nbp);       // quantized activation, MMA-operand form
+  float *rowres = act.dxs + nbp;                                                // [rmax]
+#else
   const int nbx = nbp + 2;                              // plane stride, padded by 16 bytes against bank conflicts
   uint2 *xq = reinterpret_cast<uint2 *>(smem + (size_t) S * a.stage_bytes);   // [4 planes p][nbx] {bytes of lane 2p, of lane 2p+1}
   float *dxs = reinterpret_cast<float *>(xq + (size_t) nbx * 4);              // [nbp]
   float *rowres = dxs + nbp;                                                    // [rmax]
+#endif
   double *red = reinterpret_cast<double *>(rowres + ((a.rmax + 3) & ~3));       // [32]
   uint64_t *full = reinterpret_cast<uint64_t *>(red + 32);                      // [S]
   uint64_t *empty = full + S;                                                   // [S]
@@ -399,6 +409,15 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
         }
       }
     }
+#if B200_IMMA
+    quantize_block_full_imma(v, b, act);
+  }
+  for (int b = nb + tid; b < nbp; b += nt) {        // padding blocks of a partial last quad: scale 0 on both sides = exact no-op
+#pragma unroll
+    for (int part = 0; part < 4; part++) act_zero_block(b, act, part);
+  }
+  named_bar_sync(1, nt);
+#else
     float amax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -423,7 +442,46 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
     dxs[b] = 0.0f;
   }
   named_bar_sync(1, nt);
+#endif
 
+#if B200_IMMA
+  // ---- main loop on the warp-level tensor path: LP selects the warp tile -- 1: 8 rows, 2: 16 rows, 4: 2 x 16 rows ----
+  {
+    constexpr int RW = LP == 1 ? 8 : 16, NT = LP == 4 ? 2 : 1;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2;
+    const int ntiles = (R + RW - 1) / RW;
+    const bool warp_active = warp * NT < ntiles;
+    int row[NT][RW / 8], lrow[NT];
+    imma_tile_rows<RW, NT>(warp * NT, lane, R, row, lrow);
+    uint32_t sel0, sel1;
+    imma_selectors(lane, sel0, sel1);
+    u64 acc[NT][RW / 8];
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+      for (int h = 0; h < RW / 8; h++) acc[i][h] = pack_f2(0.0f, 0.0f);
+    for (int k = 0; k < nchunks; k++) {
+      const int s = k % S;
+      mbar_wait(&full[s], (k / S) & 1);
+      if (warp_active) {
+        const int cqk = min(cq, nbq - k * cq);
+        gemv_chunk_imma<RW, NT>(stages + (size_t) s * a.stage_bytes, cqk, R, row, lrow, lane, act, k * a.cb, sel0, sel1, acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+      for (int h = 0; h < RW / 8; h++) {
+        const u64 one[1] = {acc[i][h]};
+        const float res = row_hsum<1>(one);
+        const int r = (warp * NT + i) * RW + g + 8 * h;
+        if ((lane & 3) == 0 && r < R) rowres[r] = res;
+      }
+    named_bar_sync(1, nt);
+  }
+#else
   // ---- main loop: 8 exact AVX2 lanes per row, LP lane-pairs per thread, one row per thread ----
   const int u = tid;
   const bool active = u < R * UPR;
@@ -444,6 +502,7 @@ __global__ void __launch_bounds__(544, 1) q4_gemv_kernel(const GemvArgs a) {
   const float res = row_hsum<LP>(acc[0]);
   if (active && pg == 0) rowres[r] = res;
   named_bar_sync(1, nt);
+#endif
 
   gemv_epilogue<EPI>(a, rp, rowres, tid, nt);
 }
@@ -604,6 +663,7 @@ __global__ void __launch_bounds__(1024, 1) argmax_advance_kernel(const float *lo
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int) (blockDim.x >> 5); w++)
       if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+    if (idx < 0 || idx >= n_vocab) idx = 0;          // all-NaN logits: never index the embedding table out of bounds
     const int step = sp->step;
     token_log[step] = idx;
     sp->token = forced_tokens ? forced_tokens[step] : idx;   // teacher forcing when a token stream is supplied
@@ -631,7 +691,7 @@ __global__ void repack_q4_0_kernel(const uint8_t *src, uint8_t *dst, int M, int 
   uint8_t *quad = dst + (size_t) rp.row0 * nbq * 80 + (size_t) k * cq * R * 80 + (size_t) ql * R * 80;
   uint32_t *dn = reinterpret_cast<uint32_t *>(quad);
   float *ds = reinterpret_cast<float *>(quad + (size_t) R * 64) + r * 4 + bq;
-  const int upr = 4 / lp;
+  const int upr = lp ? 4 / lp : 4;
   uint32_t wout[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u};
   float d = 0.0f;
   if (gr < M && b < nb) {
@@ -653,6 +713,18 @@ __global__ void repack_q4_0_kernel(const uint8_t *src, uint8_t *dst, int M, int 
       }
       wout[p] = wv;
     }
+  }
+  if (lp == 0) {
+    // tensor-path row loop (rowloop_imma.cuh): the block's 16 nibble bytes in ggml's own order, word t = bytes 4t..4t+3
+    uint32_t raw[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u};
+    if (gr < M && b < nb) {
+      const uint32_t *sp = reinterpret_cast<const uint32_t *>(src + ((size_t) (interleave_half > 0 ? ((gr & 1) ? interleave_half + gr / 2 : gr / 2) : gr) * nb + b) * 20);
+      raw[0] = sp[1]; raw[1] = sp[2]; raw[2] = sp[3]; raw[3] = sp[4];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) dn[((size_t) bq * R + r) * 4 + t] = raw[t];      // [block][row][16 bytes]
+    *ds = d;
+    return;
   }
 #pragma unroll
   for (int p = 0; p < 4; p++) {

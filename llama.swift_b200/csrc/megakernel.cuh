@@ -242,9 +242,13 @@ __device__ __forceinline__ void plain_read_rounds(const float *src, int items, i
 
 struct MegaSmem {
   uint8_t *stages;
+#if B200_IMMA
+  ActSmem act;      // quantized activation vector in MMA-operand form (rowloop_imma.cuh)
+#else
   uint2 *xq;        // [4 planes p][nb_max] {signed bytes of lane 2p, of lane 2p+1} of every block
   int nbx;          // plane stride = nb_max + 2 (bank-conflict padding)
   float *dxs;       // [nb_max]
+#endif
   float *xs;        // [xs_floats] attention scores / probabilities
   float *rowres;    // [MEGA_MAX_ROWS]
   double *redd;     // [2][16]
@@ -353,8 +357,12 @@ __device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int 
 __device__ __forceinline__ void zero_pad_blocks(int nb, const MegaSmem &sm, int tid) {
   const int nbp = (nb + 3) & ~3;
   if (tid < (nbp - nb) * 4) {
+#if B200_IMMA
+    act_zero_block(nb + (tid >> 2), sm.act, tid & 3);
+#else
     sm.xq[(tid & 3) * sm.nbx + nb + (tid >> 2)] = make_uint2(0u, 0u);
     if ((tid & 3) == 0) sm.dxs[nb + (tid >> 2)] = 0.0f;
+#endif
   }
 }
 
@@ -407,7 +415,11 @@ __device__ __forceinline__ void prologue_plain_batch(const uint2 *src, bool plai
     const int it = it0 + tid + rd * MEGA_COMPUTE_THREADS;
     const bool live = it < items;         // a block's 4 quarter-items are all live or all padding (512 % 4 == 0)
     const int iq = rot_item(it, items, rot);
+#if B200_IMMA
+    quantize_block_4t_imma(v[rd], iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.act);
+#else
     quantize_block_4t(v[rd], iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.nbx, sm.dxs);
+#endif
   }
 }
 
@@ -477,7 +489,7 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
   const double var = pow2 ? __dmul_rn(s2, invK) : s2 / (double) K;
   const float nscale = (float) (1.0 / sqrt(__dadd_rn(var, (double) 1e-5f)));               // ggml.c:5379
 #if B200_PROF_LN
-  if (nscale == 123.456f) sm.dxs[0] = nscale;   // keeps the mark below after the division (never true in practice)
+  if (nscale == 123.456f) sm.rowres[0] = nscale;   // keeps the mark below after the division (never true in practice)
 #endif
   LN_MARK();
 #pragma unroll
@@ -490,7 +502,11 @@ __device__ __forceinline__ void prologue_norm_regs(double (&xd)[MEGA_NORM_ROUNDS
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) v[i] = __fmul_rn(w[i], __fmul_rn((float) xd[rd][i], nscale));   // y = (float)v; y *= scale; w*y
+#if B200_IMMA
+      quantize_block_4t_imma(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.act);
+#else
       quantize_block_4t(v, iq >> 2, live ? (iq & 3) : 4 + (iq & 3), sm.xq, sm.nbx, sm.dxs);
+#endif
     }
   }
   zero_pad_blocks(nb, sm, tid);
@@ -539,6 +555,57 @@ struct RingPos {
   __device__ __forceinline__ void next(int S) { g++; if (++s == S) { s = 0; par ^= 1u; } }
 };
 
+#if B200_IMMA
+// Tensor-path row loop: warp w owns tiles w*NT .. w*NT+NT-1 of RW rows (RW = 8: rows g of the MMA tile only).
+template <int RW, int NT>
+__device__ __forceinline__ void gemv_rows_imma(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
+                                               int S, int stage_bytes, int tid) {
+  const int R = rp.R, cb = md.cb;
+  const int nbq = (md.nb + 3) >> 2, cq = cb >> 2;
+  const int nchunks = (nbq + cq - 1) / cq;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2;
+  const int ntiles = (R + RW - 1) / RW;
+  const bool warp_active = warp * NT < ntiles;         // warps with no rows skip the math but still release stages
+  int row[NT][RW / 8], lrow[NT];
+  imma_tile_rows<RW, NT>(warp * NT, lane, R, row, lrow);
+  uint32_t sel0, sel1;
+  imma_selectors(lane, sel0, sel1);
+  u64 acc[NT][RW / 8];
+#pragma unroll
+  for (int i = 0; i < NT; i++)
+#pragma unroll
+    for (int h = 0; h < RW / 8; h++) acc[i][h] = pack_f2(0.0f, 0.0f);
+
+  for (int k = 0; k < nchunks; k++, ring.next(S)) {
+    const int s = ring.s;
+    mbar_wait(&sm.full[s], ring.par);
+    if (warp_active && !B200_NO_MATH) {
+      const int cqk = min(cq, nbq - k * cq);
+      gemv_chunk_imma<RW, NT>(sm.stages + (size_t) s * stage_bytes, cqk, R, row, lrow, lane, sm.act, k * cb, sel0, sel1, acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[s]);
+  }
+#pragma unroll
+  for (int i = 0; i < NT; i++)
+#pragma unroll
+    for (int h = 0; h < RW / 8; h++) {
+      const u64 one[1] = {acc[i][h]};
+      const float res = row_hsum<1>(one);
+      const int r = (warp * NT + i) * RW + g + 8 * h;
+      if ((lane & 3) == 0 && r < R) sm.rowres[r] = res;
+    }
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
+}
+
+// md.lp = rows per warp tile (8 / 16), md.rpt = tiles per warp (1 / 2) -- chosen by the host plan (engine.cu: make_plan)
+__device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
+                                              int S, int stage_bytes, int tid) {
+  if (md.lp == 8) gemv_rows_imma<8, 1>(md, rp, sm, ring, S, stage_bytes, tid);
+  else if (md.rpt == 1) gemv_rows_imma<16, 1>(md, rp, sm, ring, S, stage_bytes, tid);
+  else gemv_rows_imma<16, 2>(md, rp, sm, ring, S, stage_bytes, tid);
+}
+#else
 template <int LP, int RPT>
 __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                           int S, int stage_bytes, int tid) {
@@ -587,6 +654,7 @@ __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart r
     default: gemv_rows<4, 1>(md, rp, sm, ring, S, stage_bytes, tid); break;
   }
 }
+#endif
 
 // ---- attention phase for (head h, output quarter qr): K.Q for all positions, soft_max, V.P for 32 dims --------------
 __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerDesc &L, const MegaSmem &sm, int h, int qr,
@@ -751,11 +819,16 @@ __device__ __forceinline__ MegaSmem carve_smem(const TokenArgs &a) {
   const int nb_max = ((max(a.n_embd, a.n_ff) / 32) + 3) & ~3;   // whole quads
   MegaSmem sm;
   sm.stages = smem_mega;
+#if B200_IMMA
+  sm.act = act_carve(smem_mega + (size_t) S * a.stage_bytes, nb_max);
+  sm.xs = sm.act.dxs + nb_max;
+#else
   sm.xq = reinterpret_cast<uint2 *>(smem_mega + (size_t) S * a.stage_bytes);
   sm.nbx = nb_max + 2;      // plane stride padded by 16 bytes: the 4 planes a quarter-warp reads together fall into
                             // different banks (an unpadded power-of-two stride made every activation load a 4-way conflict)
   sm.dxs = reinterpret_cast<float *>(sm.xq + (size_t) sm.nbx * 4);
   sm.xs = sm.dxs + nb_max;
+#endif
   sm.rowres = sm.xs + a.xs_floats;
   sm.redd = reinterpret_cast<double *>(sm.rowres + MEGA_MAX_ROWS);
   sm.redf = reinterpret_cast<float *>(sm.redd + 32);

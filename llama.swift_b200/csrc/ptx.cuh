@@ -37,6 +37,28 @@ __device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c) 
   uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
 
+// D(16x8, s32) = A(16x32, u8, row) * B(32x8, s8, col) + C on the warp-level tensor path (SASS IMMA.16832.U8.S8).
+// Fragment owner: lane = 4*g + t.  a0 = A[g][4t..4t+3], a1 = A[g+8][4t..], a2 = A[g][16+4t..], a3 = A[g+8][16+4t..];
+// b0 = B[4t..4t+3][g], b1 = B[16+4t..][g]; d0,d1 = D[g][2t, 2t+1], d2,d3 = D[g+8][2t, 2t+1].
+__device__ __forceinline__ void mma_u8s8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1, int c) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c));
+}
+// 8x8 b16 matrices from shared memory in MMA fragment order (SASS LDSM): lane i gets bytes 4(i%4)..4(i%4)+3 of row i/4;
+// lanes 0-7 supply the 16-byte row addresses of matrix 0, lanes 8-15 of matrix 1 (x2)
+__device__ __forceinline__ void ldmatrix_x2(uint32_t &r0, uint32_t &r1, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_addr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x1(uint32_t &r0, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(smem_addr) : "memory");
+}
+// byte permute: result byte i = byte sel[4i+3:4i] of {b (bytes 4-7), a (bytes 0-3)}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
