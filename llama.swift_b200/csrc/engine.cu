@@ -297,11 +297,14 @@ struct b200_llama {
   unsigned int *d_epoch = nullptr;
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1;
+  int fold_argmax = 0;                     // this launch folds the greedy pick into the token kernel (decode_device)
+  float2 *d_am = nullptr;                  // per-CTA arg-max candidates
   double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
   std::vector<cudaEvent_t> kev;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
+  const void *graph_log = nullptr, *graph_forced = nullptr;   // buffers baked into the captured kernel parameters
 };
 
 namespace {
@@ -317,6 +320,11 @@ MatDesc mat_desc(const GemvPlan &p) {
   return d;
 }
 
+bool mega_usable(const b200_llama *m, int n_threads);
+bool fold_usable(const b200_llama *m, int n_threads) {
+  return m->opt_fold && m->tp_size == 1 && mega_usable(m, n_threads);
+}
+
 bool mega_usable(const b200_llama *m, int n_threads) {
   return (m->opt_mega || m->tp_size > 1) && m->f16 == 2 && m->mega_S >= 2 && n_threads <= MEGA_MAX_NTH;
 }
@@ -329,6 +337,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.n_layer = m->n_layer; a.out = mat_desc(m->out); a.final_norm = m->d_norm;
   a.tok_emb = m->d_tok_emb; a.q = m->d_q;
   a.rope = m->d_rope; a.silu_table = m->d_silu; a.exp_table = m->d_exp; a.sp = m->d_sp;
+  a.fold_argmax = m->fold_argmax; a.am = m->d_am; a.token_log = m->d_token_log; a.forced_tokens = m->d_forced;
   a.tp.rank = m->tp_rank; a.tp.size = m->tp_size; a.tp.e_loc = m->e_loc; a.tp.f_loc = m->f_loc; a.tp.v_loc = m->v_loc;
   for (int p = 0; p < m->tp_size; p++) {
     uint8_t *base = m->peer_xchg[p];
@@ -436,8 +445,9 @@ cudaError_t enqueue_token(b200_llama *m, int n_threads, bool pdl, long long *lau
 cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
   const bool pdl = m->opt_pdl != 0;
   if (!m->opt_graph) return enqueue_token(m, n_threads, pdl, launches);
-  const int key_pdl = (int) pdl | (mega_usable(m, n_threads) ? 2 : 0);
-  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != key_pdl) {
+  const int key_pdl = (int) pdl | (mega_usable(m, n_threads) ? 2 : 0) | (m->fold_argmax ? 4 : 0);
+  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != key_pdl ||
+      (m->fold_argmax && (m->graph_log != m->d_token_log || m->graph_forced != m->d_forced))) {
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
@@ -452,6 +462,7 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
     if (e != cudaSuccess) return e;
     m->graph_threads = n_threads;
     m->graph_pdl = key_pdl;
+    m->graph_log = m->d_token_log; m->graph_forced = m->d_forced;
   }
   if (launches) *launches += mega_usable(m, n_threads) ? 1 : 2 + 5LL * m->n_layer;
   return cudaGraphLaunch(m->graph_exec, m->stream);
@@ -507,7 +518,7 @@ void free_model(b200_llama *m) {
   cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h);   // d_logits lives inside d_xchg
-  delete m->h_token_args; cudaFree(m->d_bar);
+  delete m->h_token_args; cudaFree(m->d_bar); cudaFree(m->d_am);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -793,6 +804,7 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     m->h_token_args = new TokenArgs();
     memset(m->h_token_args, 0, sizeof(TokenArgs));
     if (m->n_layer <= MEGA_MAX_LAYERS) memcpy(m->h_token_args->layers, descs.data(), descs.size() * sizeof(LayerDesc));
+    CUDA_TRY(cudaMalloc(&m->d_am, (size_t) std::max(1, m->n_sm) * sizeof(float2)));
     CUDA_TRY(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned int)));
     // shared-memory budget of the whole-token kernel: fixed areas first, the rest is the weight ring
@@ -928,7 +940,7 @@ static std::vector<b200_llama *> ranks_of(b200_llama *m) {
 static int eval_enqueue_token(b200_llama *m, int n_threads, int token, int pos, int p_part, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
-  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, p_part, 0);
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, p_part, 0, 0);
   CUDA_TRY(cudaGetLastError());
   m->last_launches++;
   CUDA_TRY(run_token(m, n_threads, &m->last_launches));
@@ -1000,11 +1012,11 @@ static int decode_prepare(b200_llama *m, int n_steps, const int32_t *forced_toke
   return B200_LLAMA_OK;
 }
 
-static int decode_begin(b200_llama *m, int n_past, int first_token, char *err, size_t errlen) {
+static int decode_begin(b200_llama *m, int n_past, int first_token, bool forced, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
   m->last_launches = 0;
-  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0);
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, first_token, n_past, n_past + 1, 0, forced ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
   return B200_LLAMA_OK;
@@ -1014,14 +1026,19 @@ static int decode_step(b200_llama *m, int n_threads, int i, bool forced, bool wa
   const int fail_code = B200_LLAMA_ERR_PREDICT;
   CUDA_TRY(cudaSetDevice(m->device));
   if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i], m->stream));
+  const bool fold = fold_usable(m, n_threads);      // the greedy pick runs inside the token kernel (one launch per token)
+  m->fold_argmax = fold ? 1 : 0;
   CUDA_TRY(run_token(m, n_threads, &m->last_launches));
+  m->fold_argmax = 0;
   if (m->opt_time_kernel) CUDA_TRY(cudaEventRecord(m->kev[2 * i + 1], m->stream));
   if (want_logits) {
     CUDA_TRY(cudaMemcpyAsync(m->d_logits_log + (size_t) i * m->n_vocab, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToDevice, m->stream));
   }
-  argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced ? m->d_forced : nullptr);
-  CUDA_TRY(cudaGetLastError());
-  m->last_launches++;
+  if (!fold) {
+    argmax_advance_kernel<<<1, 1024, 0, m->stream>>>(m->d_logits, m->n_vocab, m->d_sp, m->d_token_log, forced ? m->d_forced : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    m->last_launches++;
+  }
   return B200_LLAMA_OK;
 }
 
@@ -1049,7 +1066,7 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
     if (rc != B200_LLAMA_OK) return rc;
   }
   for (b200_llama *r : ranks) {
-    const int rc = decode_begin(r, n_past, first_token, err, errlen);
+    const int rc = decode_begin(r, n_past, first_token, forced_tokens != nullptr, err, errlen);
     if (rc != B200_LLAMA_OK) return rc;
   }
   // step-major enqueue (see b200_llama_eval): rank 0's step i must not be queued behind hundreds of its own later steps
@@ -1234,7 +1251,7 @@ int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, l
   if (cudaMalloc(&m->d_prof, (size_t) marks * m->n_sm * 8) != cudaSuccess) return -3;
   cudaMemset(m->d_prof, 0, (size_t) marks * m->n_sm * 8);
   m->prof_marks = marks;
-  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, pos + 1, 0);
+  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, pos + 1, 0, 0);
   long long dummy = 0;
   cudaError_t e = enqueue_token_mega(m, n_threads, &dummy);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
@@ -1252,6 +1269,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "pdl")) { m->opt_pdl = value; return 0; }
   if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
   if (!strcmp(key, "time_kernel")) { m->opt_time_kernel = value; return 0; }
+  if (!strcmp(key, "fold_argmax")) { m->opt_fold = value; return 0; }
   return -1;
 }
 

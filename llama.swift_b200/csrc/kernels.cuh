@@ -35,6 +35,7 @@ struct StepParams {
   int pos;      // its position = n_past + i
   int p_part;   // n_past + N of the enclosing llama_eval call: the reference partitions V.P columns by it (ggml.c:5628)
   int step;     // running index for the greedy loop's token log
+  int forced;   // != 0: the device-resident loop feeds forced_tokens[step] next (teacher forcing) instead of the arg-max
 };
 
 // ---- row partition of a (fused) matrix over the grid: granules of 4 rows, contiguous, balanced ------------------
@@ -82,6 +83,17 @@ __device__ __forceinline__ int lane_elem(int lane, int k) { return (k < 2 ? 0 : 
 #ifndef B200_PIPE
 #define B200_PIPE 1         // small register footprints: two quads in registers, loads of quad q+1 issued under the math of quad q
 #endif
+
+#ifndef B200_SHF
+#define B200_SHF 0          // 1 = the nibble shift as a funnel shift (SASS SHF, ALU pipe) instead of ptxas' IMAD.SHL (FMA pipe, the busy one)
+#endif
+__device__ __forceinline__ uint32_t shl4(uint32_t w) {
+#if B200_SHF
+  uint32_t d; asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(w), "r"(4u)); return d;
+#else
+  return w << 4;
+#endif
+}
 
 template <int LP, int RPT>
 struct QuadRegs {
@@ -140,7 +152,7 @@ __device__ __forceinline__ void quad_math(const QuadRegs<LP, RPT> &q, u64 (&acc)
         const int xlo = (int) ((b & 1) ? xv.z : xv.x), xhi = (int) ((b & 1) ? xv.w : xv.y);
 #if B200_LOP3
         const int a_hi = (int) and_xor(w, 0xF0F0F0F0u, 0x80808080u);             // signed bytes 16*(q-8), lane 2p+1
-        const int a_lo = (int) and_xor(w << 4, 0xF0F0F0F0u, 0x80808080u);        // signed bytes 16*(q-8), lane 2p
+        const int a_lo = (int) and_xor(shl4(w), 0xF0F0F0F0u, 0x80808080u);       // signed bytes 16*(q-8), lane 2p
 #else
         const int a_hi = (int) ((w & 0xF0F0F0F0u) ^ 0x80808080u);                // signed bytes 16*(q-8), lane 2p+1
         const int a_lo = (int) (((w << 4) & 0xF0F0F0F0u) ^ 0x80808080u);         // signed bytes 16*(q-8), lane 2p
@@ -633,10 +645,10 @@ __global__ void embed_kernel(const uint8_t *tok_emb_raw, const StepParams *sp, f
   out[e] = __fmul_rn((float) (qn - 8), d);
 }
 
-__global__ void set_step_kernel(StepParams *sp, int token, int pos, int p_part, int step) {
+__global__ void set_step_kernel(StepParams *sp, int token, int pos, int p_part, int step, int forced) {
   pdl_launch_dependents();
   pdl_wait();
-  sp->token = token; sp->pos = pos; sp->p_part = p_part; sp->step = step;
+  sp->token = token; sp->pos = pos; sp->p_part = p_part; sp->step = step; sp->forced = forced;
 }
 
 // greedy pick (first maximum, like numpy.argmax) + advance the step scalars; feeds the next graph replay

@@ -101,8 +101,15 @@ struct TokenArgs {
   long long spin_limit;     // clock64 ticks before a spin-wait traps instead of hanging the box
   const double2 *rope;
   const uint16_t *silu_table, *exp_table;
-  const StepParams *sp;
-  unsigned int *bar;        // [0] unused, [1] end-of-token CTA counter (tensor-parallel groups); zeroed before every launch
+  StepParams *sp;           // read at kernel start; advanced by the folded arg-max (below) at the very end
+  // Greedy pick folded into the token kernel (single GPU, device-resident loop): every CTA reduces its own logits rows,
+  // the last CTA to finish reduces the per-CTA candidates, logs the token and advances the step scalars -- what the
+  // separate arg-max kernel did in one more launch per token (19.5 us under ncu, profiles/r1_f_launches_bench.md).
+  int fold_argmax;
+  float2 *am;               // [gridDim.x] {value, index bits} candidate of every CTA
+  int *token_log;
+  const int *forced_tokens;
+  unsigned int *bar;        // [0] arg-max CTA counter, [1] end-of-token CTA counter (tensor-parallel groups); zeroed before every launch
   int n_embd, n_head, n_ctx, n_ff, n_threads;
   float kq_scale;
   int S, stage_bytes;
@@ -1182,6 +1189,72 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     }
   } else if (blockIdx.x == 0 && tid == 0) {
     *a.epoch = epoch + 1u;       // every CTA read the old value before CTA 0 can get here (it needed their rows)
+  }
+  if (a.fold_argmax && T == 1) {
+    // ---- greedy pick (first maximum, like numpy.argmax): this CTA's rows are still in sm.rowres ----
+    const RowPart rp = row_part(a.out.g_total, gridDim.x, blockIdx.x);
+    float best = -CUDART_INF_F;
+    int idx = 0x7fffffff;
+    for (int i = tid; i < rp.R; i += MEGA_COMPUTE_THREADS) {
+      const int g = rp.row0 + i;
+      if (g < a.out.M) {
+        const float v = sm.rowres[i];
+        if (v > best || (v == best && g < idx)) { best = v; idx = g; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    float *cv = sm.redf;                                  // [16] values | [16] indices (as int bits)
+    int *ci = reinterpret_cast<int *>(sm.redf + 16);
+    named_bar_sync(1, MEGA_COMPUTE_THREADS);             // everybody is done with redf / rowres of the phases
+    if ((tid & 31) == 0) { cv[tid >> 5] = best; ci[tid >> 5] = idx; }
+    named_bar_sync(1, MEGA_COMPUTE_THREADS);
+    if (tid < 32) {
+      best = tid < MEGA_COMPUTE_WARPS ? cv[tid] : -CUDART_INF_F;
+      idx = tid < MEGA_COMPUTE_WARPS ? ci[tid] : 0x7fffffff;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+      }
+      unsigned int old = 0;
+      if (tid == 0) {
+        a.am[blockIdx.x] = make_float2(best, __int_as_float(idx));
+        __threadfence();
+        old = atomicAdd(a.bar, 1u);
+      }
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == gridDim.x - 1) {                         // the last CTA: every candidate is visible
+        __threadfence();
+        best = -CUDART_INF_F; idx = 0x7fffffff;
+        for (int c = tid; c < (int) gridDim.x; c += 32) {
+          const float2 cand = __ldcg(a.am + c);
+          const int oi = __float_as_int(cand.y);
+          if (cand.x > best || (cand.x == best && oi < idx)) { best = cand.x; idx = oi; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+          if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+        }
+        if (tid == 0) {
+          if (idx < 0 || idx >= a.out.M) idx = 0;         // all-NaN logits: never index the embedding table out of bounds
+          StepParams *sp = a.sp;
+          const int step = sp->step;
+          a.token_log[step] = idx;
+          sp->token = sp->forced ? a.forced_tokens[step] : idx;
+          sp->pos += 1;
+          sp->p_part += 1;
+          sp->step = step + 1;
+        }
+      }
+    }
   }
 }
 

@@ -268,13 +268,14 @@ def test_resident_model_cache(small_model):
     h1 = a._h.value
     busy = lsb.llama_model_acquire(small_model, n_ctx=64)       # `a` is in use: a concurrent operation gets its own model
     assert busy._h.value != h1
+    h2 = busy._h.value
     busy.release()
     a.release()
     t0 = time.perf_counter()
     b = lsb.llama_model_acquire(small_model, n_ctx=64)
     t_again = time.perf_counter() - t0
     try:
-        assert b._h.value == h1                                    # the resident model, not a fresh load
+        assert b._h.value in (h1, h2)                              # a resident model (one idle copy is kept), not a fresh load
         again = lsb.llama_eval(b, 8, 0, toks)
         assert np.array_equal(bits(again), bits(first))
         assert np.array_equal(bits(lsb.llama_eval(b, 8, 5, np.array([int(first.argmax())], np.int32))), bits(step))
