@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "kernels_q4_1.cuh"
 #include "megakernel.cuh"
+#include "batch.cuh"
 
 namespace b200 {
 void host_build_tables(uint16_t *table_silu_f16, uint16_t *table_exp_f16);
@@ -216,6 +217,10 @@ cudaError_t configure_kernels() {
   if ((e = configure_gemv<PRO_NORM, EPI_STORE>()) != cudaSuccess) return e;
   if ((e = configure_gemv<PRO_PLAIN, EPI_STORE>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(decode_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(batch_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
@@ -297,7 +302,12 @@ struct b200_llama {
   unsigned int *d_epoch = nullptr;
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1, opt_batch = 1;
+  // prompt batches (batch.cuh): per-chunk activation buffers, allocated on first use
+  int batch_cap = 0;
+  float *b_x = nullptr, *b_ff = nullptr, *b_q = nullptr, *b_att = nullptr, *b_h = nullptr, *b_o = nullptr;
+  uint8_t *b_act = nullptr;
+  int *b_tok = nullptr;
   int fold_argmax = 0;                     // this launch folds the greedy pick into the token kernel (decode_device)
   float2 *d_am = nullptr;                  // per-CTA arg-max candidates
   double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
@@ -519,6 +529,7 @@ void free_model(b200_llama *m) {
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h);   // d_logits lives inside d_xchg
   delete m->h_token_args; cudaFree(m->d_bar); cudaFree(m->d_am);
+  cudaFree(m->b_x); cudaFree(m->b_ff); cudaFree(m->b_q); cudaFree(m->b_att); cudaFree(m->b_h); cudaFree(m->b_o); cudaFree(m->b_act); cudaFree(m->b_tok);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -934,6 +945,105 @@ static std::vector<b200_llama *> ranks_of(b200_llama *m) {
   return m->group.empty() ? std::vector<b200_llama *>{m} : m->group;
 }
 
+
+// ---- prompt batches (batch.cuh) ------------------------------------------------------------------------------------------
+constexpr int kBatchChunk = 256;      // tokens evaluated together (bounds the activation buffers: ~210 KB per token at 7B)
+
+bool batch_usable(const b200_llama *m, int n_tokens) {
+  return m->opt_batch && n_tokens >= 2 && m->f16 == 2 && m->tp_size == 1 && !B200_IMMA;
+}
+
+cudaError_t batch_reserve(b200_llama *m, int n) {
+  if (m->batch_cap >= n) return cudaSuccess;
+  cudaFree(m->b_x); cudaFree(m->b_ff); cudaFree(m->b_q); cudaFree(m->b_att); cudaFree(m->b_h); cudaFree(m->b_o); cudaFree(m->b_act); cudaFree(m->b_tok);
+  m->b_x = m->b_ff = m->b_q = m->b_att = m->b_h = m->b_o = nullptr; m->b_act = nullptr; m->b_tok = nullptr; m->batch_cap = 0;
+  const size_t E = m->n_embd, F = m->n_ff;
+  cudaError_t e;
+  if ((e = cudaMalloc(&m->b_x, (size_t) n * E * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_ff, (size_t) n * E * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_q, (size_t) n * E * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_att, (size_t) n * E * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_h, (size_t) n * F * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_o, (size_t) n * std::max(3 * E, 2 * F) * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_act, (size_t) n * batch_act_bytes((int) (std::max(E, F) / 32)))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&m->b_tok, (size_t) n * 4)) != cudaSuccess) return e;
+  m->batch_cap = n;
+  return cudaSuccess;
+}
+
+// out[n][ld] = W (plan p) x the n prepared activation vectors in m->b_act: weights streamed once per BATCH_NC columns
+cudaError_t launch_gemm_cols(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches) {
+  GemmColsArgs a = {};
+  a.w = p.d_w; a.M = p.M; a.g_total = p.g_total; a.nb = p.nb; a.cb = p.cb; a.stage_bytes = p.stage_bytes; a.rmax = p.rmax;
+  a.act = m->b_act; a.out = out; a.ld_out = ld_out; a.N = n;
+  const int nbp = (p.nb + 3) & ~3;
+  const size_t col_bytes = (size_t) (nbp + 2) * 32 + (size_t) nbp * 4;
+  const long ring = (long) kSmemBudget - (long) (BATCH_NC * col_bytes) - 256;
+  const int nchunks = ((p.nb + 3) / 4 + p.cb / 4 - 1) / (p.cb / 4);
+  int S = (int) (ring / (p.stage_bytes + 16));
+  if (S < 1) return cudaErrorInvalidConfiguration;
+  S = std::min(S, nchunks);
+  a.n_stages = S;
+  const size_t smem = (size_t) S * p.stage_bytes + BATCH_NC * col_bytes + (size_t) 2 * S * 8;
+  const dim3 grid(p.n_cta, (n + BATCH_NC - 1) / BATCH_NC), block(p.threads);
+  switch (p.lp) {
+    case 1: q4_gemm_cols_kernel<1><<<grid, block, smem, m->stream>>>(a); break;
+    case 2: q4_gemm_cols_kernel<2><<<grid, block, smem, m->stream>>>(a); break;
+    default: q4_gemm_cols_kernel<4><<<grid, block, smem, m->stream>>>(a); break;
+  }
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// llama_eval for tokens [t0, t0 + n) of a call with n_call tokens in total (PO.mm:510-735, N > 1)
+cudaError_t enqueue_batch_chunk(b200_llama *m, int n_threads, int n_past_call, int n_call, int t0, int n, const int32_t *tokens,
+                                bool last_chunk, long long *launches) {
+  cudaStream_t st = m->stream;
+  cudaError_t e;
+  const int E = m->n_embd, F = m->n_ff, hd = E / m->n_head;
+  const int n_past = n_past_call + t0;
+  long long nl = 0;
+  if ((e = cudaMemcpyAsync(m->b_tok, tokens + t0, (size_t) n * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+  batch_embed_kernel<<<dim3((E + 255) / 256, n), 256, 0, st>>>(m->d_tok_emb, m->b_tok, m->b_x, E);
+  nl++;
+  auto ew = [](size_t total) { return (unsigned) ((total + 255) / 256); };
+  for (int il = 0; il < m->n_layer; il++) {
+    b200_llama::Layer &L = m->layers[il];
+    float *k_layer = m->d_k + (size_t) il * m->n_ctx * E;
+    float *v_layer = m->d_v + (size_t) il * m->n_ctx * E;
+    batch_prep_kernel<1><<<n, 256, 0, st>>>(m->b_x, L.attn_norm, m->b_act, E);                       // PO.mm:570-575
+    if ((e = launch_gemm_cols(m, L.qkv, n, m->b_o, 3 * E, &nl)) != cudaSuccess) return e;           // PO.mm:579-583
+    batch_qkv_kernel<<<dim3((3 * E / 2 + 255) / 256, n), 256, 0, st>>>(m->b_o, n_past, m->b_q, k_layer, v_layer, m->d_rope, E, hd);
+    {
+      BatchAttnArgs a = {};
+      a.q = m->b_q; a.k_layer = k_layer; a.v_layer = v_layer; a.out = m->b_att; a.exp_table = m->d_exp;
+      a.n_embd = E; a.n_threads = n_threads; a.n_ctx = m->n_ctx; a.n_past = n_past; a.N = n_past_call + n_call - n_past;
+      a.kq_scale = m->kq_scale;
+      batch_attn_kernel<<<dim3(m->n_head * ATTN_CLUSTER, n), ATTN_THREADS, attn_smem_bytes(m, n_threads), st>>>(a);   // PO.mm:614-646
+    }
+    batch_prep_kernel<0><<<n, 256, 0, st>>>(m->b_att, nullptr, m->b_act, E);
+    if ((e = launch_gemm_cols(m, L.wo, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:649-651
+    batch_resid_kernel<<<ew((size_t) n * E), 256, 0, st>>>(m->b_o, m->b_x, m->b_ff, (size_t) n * E);    // PO.mm:654
+    batch_prep_kernel<1><<<n, 256, 0, st>>>(m->b_ff, L.ffn_norm, m->b_act, E);                        // PO.mm:660-665
+    if ((e = launch_gemm_cols(m, L.w13, n, m->b_o, 2 * F, &nl)) != cudaSuccess) return e;           // PO.mm:668-676
+    batch_silu_kernel<<<ew((size_t) n * F), 256, 0, st>>>(m->b_o, m->b_h, m->d_silu, F, (size_t) n * F);   // PO.mm:678-680
+    batch_prep_kernel<0><<<n, 256, 0, st>>>(m->b_h, nullptr, m->b_act, F);
+    if ((e = launch_gemm_cols(m, L.w2, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:682-684
+    batch_resid_kernel<<<ew((size_t) n * E), 256, 0, st>>>(m->b_o, m->b_ff, m->b_x, (size_t) n * E);    // PO.mm:687
+    nl += 8;
+  }
+  if (last_chunk) {
+    // the caller gets the logits of the LAST token only (PO.mm:724-725): final norm + lm_head on one column
+    batch_prep_kernel<1><<<1, 256, 0, st>>>(m->b_x + (size_t) (n - 1) * E, m->d_norm, m->b_act, E);   // PO.mm:694-701
+    uint8_t *act_save = m->b_act;
+    if ((e = launch_gemm_cols(m, m->out, 1, m->d_logits, m->n_vocab, &nl)) != cudaSuccess) return e;  // PO.mm:705
+    (void) act_save;
+    nl += 1;
+  }
+  if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
 // One token of a batch on one rank.  The reference evaluates the N columns of every mat-mul independently, so a batch is
 // run one token at a time; p_part carries n_past + N, the one place where the batch size enters the arithmetic (V*P
 // partition, ggml.c:5628).
@@ -963,6 +1073,19 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
   if (const char *why = tp_ready(m, n_threads)) { set_err(err, errlen, "%s", why); return fail_code; }
   const std::vector<b200_llama *> ranks = ranks_of(m);
   for (b200_llama *r : ranks) r->last_launches = 0;
+  if (batch_usable(m, n_tokens)) {
+    // prompt batch: every weight row is read once per group of columns (batch.cuh), not once per token
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(batch_reserve(m, std::min(n_tokens, kBatchChunk)));
+    for (int t0 = 0; t0 < n_tokens; t0 += kBatchChunk) {
+      const int n = std::min(kBatchChunk, n_tokens - t0);
+      CUDA_TRY(enqueue_batch_chunk(m, n_threads, n_past, n_tokens, t0, n, tokens, t0 + n == n_tokens, &m->last_launches));
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
+    return B200_LLAMA_OK;
+  }
   // Token-major enqueue: the token kernels of a group wait for each other ON THE GPUS, so every rank must receive
   // token i before any rank receives so much work that the driver's launch queue blocks the host (one host thread
   // drives all ranks of a single-process group).
@@ -1270,6 +1393,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "mega")) { m->opt_mega = value; return 0; }
   if (!strcmp(key, "time_kernel")) { m->opt_time_kernel = value; return 0; }
   if (!strcmp(key, "fold_argmax")) { m->opt_fold = value; return 0; }
+  if (!strcmp(key, "batch")) { m->opt_batch = value; return 0; }
   return -1;
 }
 
