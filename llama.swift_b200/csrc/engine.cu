@@ -25,6 +25,7 @@
 #include "kernels_q4_1.cuh"
 #include "megakernel.cuh"
 #include "batch.cuh"
+#include "prefill_tc.cuh"
 
 namespace b200 {
 void host_build_tables(uint16_t *table_silu_f16, uint16_t *table_exp_f16);
@@ -59,6 +60,7 @@ struct GemvPlan {
   int qtype = 2;            // 2 = Q4_0 (20 B / 32 weights), 3 = Q4_1 (24 B / 32 weights)
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
+  uint8_t *d_wtc = nullptr;   // the same weights in the tensor-core prefill layout (prefill_tc.cuh), or null
   int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rpt = 1, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
   size_t smem = 0;
 };
@@ -221,6 +223,7 @@ cudaError_t configure_kernels() {
   if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(batch_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(q4_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
@@ -302,7 +305,10 @@ struct b200_llama {
   unsigned int *d_epoch = nullptr;
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
-  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1, opt_batch = 1;
+  int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1, opt_batch = 1, opt_tc = 1;
+  bool want_tc_copy = false;               // keep a second copy of the weights in the prefill (tcgen05) layout
+  __half *b_xh = nullptr;                  // [cap_pad][max K] fp16 quantized activations (tcgen05 operand source)
+  float *b_dxT = nullptr;                  // [max nb][cap_pad] their block scales, transposed
   // prompt batches (batch.cuh): per-chunk activation buffers, allocated on first use
   int batch_cap = 0;
   float *b_x = nullptr, *b_ff = nullptr, *b_q = nullptr, *b_att = nullptr, *b_h = nullptr, *b_o = nullptr;
@@ -508,6 +514,14 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (p.qtype == 2 && m->want_tc_copy) {
+    // second copy for the tcgen05 prefill mat-mul: 128-row tiles, one 10 KB TMA box per (tile, quad of blocks)
+    const size_t tcb = tc_weight_bytes(p.M, p.nb);
+    if ((e = cudaMalloc(&p.d_wtc, tcb)) != cudaSuccess) return e;
+    const long long total = (long long) ((p.M + TC_M - 1) / TC_M) * TC_M * ((p.nb + 3) / 4) * 4;
+    repack_prefill_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, m->stream>>>(d_stage, p.d_wtc, p.M, p.nb, interleave_half);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   m->weight_bytes += (long long) p.M * p.nb * (p.qtype == 3 ? 24 : 20);
   return cudaStreamSynchronize(m->stream);
 }
@@ -530,6 +544,9 @@ void free_model(b200_llama *m) {
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h);   // d_logits lives inside d_xchg
   delete m->h_token_args; cudaFree(m->d_bar); cudaFree(m->d_am);
   cudaFree(m->b_x); cudaFree(m->b_ff); cudaFree(m->b_q); cudaFree(m->b_att); cudaFree(m->b_h); cudaFree(m->b_o); cudaFree(m->b_act); cudaFree(m->b_tok);
+  cudaFree(m->b_xh); cudaFree(m->b_dxT);
+  for (auto &L : m->layers) { cudaFree(L.qkv.d_wtc); cudaFree(L.wo.d_wtc); cudaFree(L.w13.d_wtc); cudaFree(L.w2.d_wtc); }
+  cudaFree(m->out.d_wtc);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -730,6 +747,8 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, t.data.data(), t.data.size(), cudaMemcpyHostToDevice);
   };
+  // the tensor-core prefill path keeps a second copy of the Q4_0 weights in its own tile layout (+1x weight bytes of HBM)
+  m->want_tc_copy = QT == 2 && tp_size == 1 && env_int("B200_PREFILL_COPY", 1) != 0 && !B200_IMMA;
   const int lp_small = env_int("B200_LP_SMALL", 0), lp_qkv = env_int("B200_LP_QKV", 0), lp_w13 = env_int("B200_LP_W13", 0), lp_out = env_int("B200_LP_OUT", 0);
   m->layers.resize(m->n_layer);
   // Row split over the tensor-parallel group: rank r keeps rows [r*n/tp, (r+1)*n/tp) of every matrix (for wq/wk/wv
@@ -956,7 +975,9 @@ bool batch_usable(const b200_llama *m, int n_tokens) {
 cudaError_t batch_reserve(b200_llama *m, int n) {
   if (m->batch_cap >= n) return cudaSuccess;
   cudaFree(m->b_x); cudaFree(m->b_ff); cudaFree(m->b_q); cudaFree(m->b_att); cudaFree(m->b_h); cudaFree(m->b_o); cudaFree(m->b_act); cudaFree(m->b_tok);
+  cudaFree(m->b_xh); cudaFree(m->b_dxT);
   m->b_x = m->b_ff = m->b_q = m->b_att = m->b_h = m->b_o = nullptr; m->b_act = nullptr; m->b_tok = nullptr; m->batch_cap = 0;
+  m->b_xh = nullptr; m->b_dxT = nullptr;
   const size_t E = m->n_embd, F = m->n_ff;
   cudaError_t e;
   if ((e = cudaMalloc(&m->b_x, (size_t) n * E * 4)) != cudaSuccess) return e;
@@ -967,8 +988,35 @@ cudaError_t batch_reserve(b200_llama *m, int n) {
   if ((e = cudaMalloc(&m->b_o, (size_t) n * std::max(3 * E, 2 * F) * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&m->b_act, (size_t) n * batch_act_bytes((int) (std::max(E, F) / 32)))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&m->b_tok, (size_t) n * 4)) != cudaSuccess) return e;
+  if (m->want_tc_copy) {
+    const size_t npad = ((size_t) n + TC_T - 1) / TC_T * TC_T;
+    if ((e = cudaMalloc(&m->b_xh, npad * std::max(E, F) * 2)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&m->b_dxT, npad * (std::max(E, F) / 32) * 4)) != cudaSuccess) return e;
+  }
   m->batch_cap = n;
   return cudaSuccess;
+}
+
+cudaError_t launch_gemm_cols(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches);
+
+// The mat-mul of a batch on the tensor cores (prefill_tc.cuh): fp16 operand copy of the prepared activations, then the
+// persistent tcgen05 / TMEM kernel over (128-row tile, 16-token tile) items
+cudaError_t launch_gemm_tc(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches) {
+  const int npad = (n + TC_T - 1) / TC_T * TC_T;
+  batch_act_tc_kernel<<<dim3((p.nb + 63) / 64, npad), 64, 0, m->stream>>>(m->b_act, batch_act_bytes(p.nb), m->b_xh, m->b_dxT, p.nb, n, npad);
+  GemmTcArgs a = {};
+  a.w = p.d_wtc; a.M = p.M; a.nb = p.nb; a.xh = m->b_xh; a.dxT = m->b_dxT; a.out = out; a.ld_out = ld_out; a.N = n; a.Npad = npad;
+  a.spin_limit = 4000000000LL;
+  const int n_items = ((p.M + TC_M - 1) / TC_M) * (npad / TC_T);
+  q4_gemm_tc_kernel<<<std::min(m->n_sm, n_items), TC_THREADS, TC_SMEM, m->stream>>>(a);
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
+
+// tensor-core path for batches when the prefill copy exists; else the CUDA-core multi-column loop
+cudaError_t launch_gemm_batch(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches) {
+  if (m->opt_tc && p.d_wtc && m->b_xh && n >= 2) return launch_gemm_tc(m, p, n, out, ld_out, launches);
+  return launch_gemm_cols(m, p, n, out, ld_out, launches);
 }
 
 // out[n][ld] = W (plan p) x the n prepared activation vectors in m->b_act: weights streamed once per BATCH_NC columns
@@ -1012,7 +1060,7 @@ cudaError_t enqueue_batch_chunk(b200_llama *m, int n_threads, int n_past_call, i
     float *k_layer = m->d_k + (size_t) il * m->n_ctx * E;
     float *v_layer = m->d_v + (size_t) il * m->n_ctx * E;
     batch_prep_kernel<1><<<n, 256, 0, st>>>(m->b_x, L.attn_norm, m->b_act, E);                       // PO.mm:570-575
-    if ((e = launch_gemm_cols(m, L.qkv, n, m->b_o, 3 * E, &nl)) != cudaSuccess) return e;           // PO.mm:579-583
+    if ((e = launch_gemm_batch(m, L.qkv, n, m->b_o, 3 * E, &nl)) != cudaSuccess) return e;           // PO.mm:579-583
     batch_qkv_kernel<<<dim3((3 * E / 2 + 255) / 256, n), 256, 0, st>>>(m->b_o, n_past, m->b_q, k_layer, v_layer, m->d_rope, E, hd);
     {
       BatchAttnArgs a = {};
@@ -1022,13 +1070,13 @@ cudaError_t enqueue_batch_chunk(b200_llama *m, int n_threads, int n_past_call, i
       batch_attn_kernel<<<dim3(m->n_head * ATTN_CLUSTER, n), ATTN_THREADS, attn_smem_bytes(m, n_threads), st>>>(a);   // PO.mm:614-646
     }
     batch_prep_kernel<0><<<n, 256, 0, st>>>(m->b_att, nullptr, m->b_act, E);
-    if ((e = launch_gemm_cols(m, L.wo, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:649-651
+    if ((e = launch_gemm_batch(m, L.wo, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:649-651
     batch_resid_kernel<<<ew((size_t) n * E), 256, 0, st>>>(m->b_o, m->b_x, m->b_ff, (size_t) n * E);    // PO.mm:654
     batch_prep_kernel<1><<<n, 256, 0, st>>>(m->b_ff, L.ffn_norm, m->b_act, E);                        // PO.mm:660-665
-    if ((e = launch_gemm_cols(m, L.w13, n, m->b_o, 2 * F, &nl)) != cudaSuccess) return e;           // PO.mm:668-676
+    if ((e = launch_gemm_batch(m, L.w13, n, m->b_o, 2 * F, &nl)) != cudaSuccess) return e;           // PO.mm:668-676
     batch_silu_kernel<<<ew((size_t) n * F), 256, 0, st>>>(m->b_o, m->b_h, m->d_silu, F, (size_t) n * F);   // PO.mm:678-680
     batch_prep_kernel<0><<<n, 256, 0, st>>>(m->b_h, nullptr, m->b_act, F);
-    if ((e = launch_gemm_cols(m, L.w2, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:682-684
+    if ((e = launch_gemm_batch(m, L.w2, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:682-684
     batch_resid_kernel<<<ew((size_t) n * E), 256, 0, st>>>(m->b_o, m->b_ff, m->b_x, (size_t) n * E);    // PO.mm:687
     nl += 8;
   }
@@ -1367,21 +1415,37 @@ long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes;
 /* Development profiler: run ONE token (current step scalars) through the whole-token kernel with per-CTA globaltimer
  * stamps at every phase boundary.  out receives n_cta * marks int64 nanosecond stamps; returns marks (or < 0). */
 int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, long long *out, int cap, int *n_cta) {
-  if (!m || !mega_usable(m, n_threads) || m->tp_size > 1) return -1;
-  cudaSetDevice(m->device);
+  if (!m || !mega_usable(m, n_threads) || tp_ready(m, n_threads)) return -1;
+  // A tensor-parallel group is profiled as a whole: every rank of a single-process group runs the stamped token here; the
+  // ranks of a one-process-per-GPU group must all make this call at the same time.  The leader's stamps are returned.
+  const std::vector<b200_llama *> ranks = ranks_of(m);
   const int marks = 2 + 26 * m->n_layer + 12;
   if ((long long) marks * m->n_sm > cap) return -2;
-  if (cudaMalloc(&m->d_prof, (size_t) marks * m->n_sm * 8) != cudaSuccess) return -3;
-  cudaMemset(m->d_prof, 0, (size_t) marks * m->n_sm * 8);
-  m->prof_marks = marks;
-  set_step_kernel<<<1, 1, 0, m->stream>>>(m->d_sp, token, pos, pos + 1, 0, 0);
-  long long dummy = 0;
-  cudaError_t e = enqueue_token_mega(m, n_threads, &dummy);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  cudaError_t e = cudaSuccess;
+  for (b200_llama *r : ranks) {
+    cudaSetDevice(r->device);
+    if (cudaMalloc(&r->d_prof, (size_t) marks * r->n_sm * 8) != cudaSuccess) return -3;
+    cudaMemset(r->d_prof, 0, (size_t) marks * r->n_sm * 8);
+    r->prof_marks = marks;
+    set_step_kernel<<<1, 1, 0, r->stream>>>(r->d_sp, token, pos, pos + 1, 0, 0);
+  }
+  for (b200_llama *r : ranks) {
+    cudaSetDevice(r->device);
+    long long dummy = 0;
+    if (e == cudaSuccess) e = enqueue_token_mega(r, n_threads, &dummy);
+  }
+  for (b200_llama *r : ranks) {
+    cudaSetDevice(r->device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+  }
+  cudaSetDevice(m->device);
   if (e == cudaSuccess) e = cudaMemcpy(out, m->d_prof, (size_t) marks * m->n_sm * 8, cudaMemcpyDeviceToHost);
-  cudaFree(m->d_prof);
-  m->d_prof = nullptr;
-  m->prof_marks = 0;
+  for (b200_llama *r : ranks) {
+    cudaSetDevice(r->device);
+    cudaFree(r->d_prof);
+    r->d_prof = nullptr;
+    r->prof_marks = 0;
+  }
   if (n_cta) *n_cta = m->n_sm;
   return e == cudaSuccess ? marks : -4;
 }
@@ -1394,6 +1458,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "time_kernel")) { m->opt_time_kernel = value; return 0; }
   if (!strcmp(key, "fold_argmax")) { m->opt_fold = value; return 0; }
   if (!strcmp(key, "batch")) { m->opt_batch = value; return 0; }
+  if (!strcmp(key, "tc")) { m->opt_tc = value; return 0; }
   return -1;
 }
 

@@ -10,11 +10,14 @@ from conftest import CpuModel, bits, rel_l2
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("tc", [1, 0], ids=["tcgen05", "cuda-core-columns"])
 @pytest.mark.parametrize("n_threads", [8, 3])
-def test_batch_vs_oracle(oracle_lib, small_model, n_threads):
-    """N = 2 / 4 / 9 (the reference's own batch sizes, PO.mm:822, 885) / 17 / 64, interleaved with single tokens."""
+def test_batch_vs_oracle(oracle_lib, small_model, n_threads, tc):
+    """N = 2 / 4 / 9 (the reference's own batch sizes, PO.mm:822, 885) / 17 / 64, interleaved with single tokens; the mat-mul
+    on the tensor cores (tcgen05 + TMEM, csrc/prefill_tc.cuh) and on the CUDA-core multi-column loop."""
     ora = CpuModel(oracle_lib, "ora", small_model, 128)
     gpu = lsb.llama_model_load(small_model, n_ctx=128)
+    gpu.set_option("tc", tc)
     try:
         rng = np.random.default_rng(23)
         n_past, exact, total = 0, 0, 0
@@ -24,7 +27,7 @@ def test_batch_vs_oracle(oracle_lib, small_model, n_threads):
             got = lsb.llama_eval(gpu, n_threads, n_past, toks)
             r = rel_l2(got, want)
             same = np.array_equal(bits(got), bits(want))
-            print(f"[batch] nth={n_threads} n_past={n_past} N={n}: bit-identical={same} rel_l2={r:.3e} launches={gpu.last_launches}")
+            print(f"[batch] tc={tc} nth={n_threads} n_past={n_past} N={n}: bit-identical={same} rel_l2={r:.3e} launches={gpu.last_launches}")
             assert r <= 1e-3 and int(got.argmax()) == int(want.argmax())
             exact += int(same)
             total += 1
