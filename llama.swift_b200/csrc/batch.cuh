@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(544, 1) q4_gemm_cols_kernel(const GemmColsArgs
       const uint8_t *wbase = a.w + (size_t) rp.row0 * nbq * 80;
       for (int k = 0; k < nchunks; k++) {
         const int s = k % S;
-        if (k >= S) mbar_wait(&empty[s], ((k / S) - 1) & 1);
+        if (k >= S && !mbar_wait(&empty[s], ((k / S) - 1) & 1)) return;
         const int cqk = min(cq, nbq - k * cq);
         const uint32_t bytes = (uint32_t) cqk * R * 80;
         mbar_arrive_expect_tx(&full[s], bytes);
@@ -327,7 +327,8 @@ struct BatchAttnArgs {
   const float *v_layer;
   float *out;              // [N][n_embd] = KQV_merged (PO.mm:641-646)
   const uint16_t *exp_table;
-  int n_embd, n_threads, n_ctx, n_past, N;
+  int n_embd, n_threads, n_ctx, n_past, N;   // N: the call's tokens from this chunk's first one on (n_past + N = the call's total)
+  int N_chunk;                               // tokens in this launch
   float kq_scale;
 };
 
@@ -417,6 +418,142 @@ __global__ void __cluster_dims__(ATTN_CLUSTER, 1, 1) __launch_bounds__(ATTN_THRE
     float o = part[lane];
     for (int t = 1; t < nth; t++) o = __fadd_rn(o, part[t * 32 + lane]);
     a.out[(size_t) n * E + h * HD + rank * 32 + lane] = o;
+  }
+}
+
+
+// ---- attention for N query tokens, query-tiled: one CTA per (head, 8 consecutive query tokens) ------------------------------
+// The per-(head, token) kernel above re-reads the whole K / V history of the head for every token: 2 x 4 x (n_past + i)
+// cache lines per token and head, i.e. O(N^2) L2 traffic that dominates a 2048-token prefill.  Here a K row is loaded once
+// and dotted with 8 queries, a V element once and multiplied into 8 accumulators.  Exactness per (query, position) is kept:
+//   K.Q   lane t owns dims t, t+32, t+64, t+96 (ggml_vec_dot_f32, AVX mapping) for all 8 queries; the 32-lane reduction tree
+//         of the reference (xor 8, 16, 4, 1, 2 -- ggml.c:872-887) is done for the 8 queries at once by recursive halving:
+//         at each of the first three levels a lane keeps half of its queries and sends the other half to its partner, so the
+//         SAME pairs of partial sums are added as in the reference with 9 shuffles instead of 40;
+//   V.P   thread = output dim; the reference's per-thread column ranges are walked in order (ggml.c:5628-5665), masked
+//         positions carry probability 0 exactly as after diag_mask_inf + soft_max (fma(v, 0, acc) = acc).
+constexpr int ATT_QT = 8;
+constexpr int ATT_TILE_THREADS = 256;
+
+__host__ __device__ __forceinline__ size_t att_tile_smem(int n_ctx) { return (size_t) n_ctx * ATT_QT * 4 + 64; }
+
+__global__ void __launch_bounds__(ATT_TILE_THREADS, 3) batch_attn_tile_kernel(const BatchAttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_batt[];
+  const int h = blockIdx.x, i0 = blockIdx.y * ATT_QT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int HD = 128, NW = ATT_TILE_THREADS / 32;
+  const int E = a.n_embd;
+  const int nq = min(ATT_QT, a.N_chunk - i0);              // live queries of this tile
+  const int pmax = a.n_past + i0 + nq;                     // positions any live query may see: [0, pmax)
+  const int p_part = a.n_past + a.N;                       // the reference partitions V*P columns by the call's total (ggml.c:5628)
+  float *pT = reinterpret_cast<float *>(smem_batt);        // [position][8 queries]: scores, then probabilities (67 KB at n_ctx 2100: 3 CTAs per SM)
+
+  // ---- K.Q ----
+  float qv[ATT_QT][4];
+#pragma unroll
+  for (int qi = 0; qi < ATT_QT; qi++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) qv[qi][i] = qi < nq ? a.q[(size_t) (i0 + qi) * E + h * HD + lane + 32 * i] : 0.0f;
+  const bool bA = (lane >> 3) & 1, bB = (lane >> 4) & 1, bC = (lane >> 2) & 1;
+  const int q_mine = 4 * (int) bA + 2 * (int) bB + (int) bC;               // the query whose sum this lane ends up with
+  for (int j = warp; j < pmax; j += NW) {
+    const float *kp = a.k_layer + (size_t) j * E + h * HD + lane;
+    float kk[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) kk[i] = kp[32 * i];
+    float p[ATT_QT];
+#pragma unroll
+    for (int qi = 0; qi < ATT_QT; qi++) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; i++) s = fmaf(kk[i], qv[qi][i], s);                // GGML_F32_VEC_FMA, ggml.c:1239
+      p[qi] = s;
+    }
+    float a4[4], b2[2];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {                                               // sum[0]+sum[1], sum[2]+sum[3]   (xor 8)
+      const float send = bA ? p[k] : p[k + 4];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      a4[k] = __fadd_rn(bA ? p[k + 4] : p[k], recv);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {                                               // (..)+(..)                      (xor 16)
+      const float send = bB ? a4[k] : a4[k + 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      b2[k] = __fadd_rn(bB ? a4[k + 2] : a4[k], recv);
+    }
+    float c;
+    {                                                                           // lanes k and k+4                (xor 4)
+      const float send = bC ? b2[0] : b2[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      c = __fadd_rn(bC ? b2[1] : b2[0], recv);
+    }
+    c = __fadd_rn(c, __shfl_xor_sync(0xffffffffu, c, 1));                       // hadd
+    c = __fadd_rn(c, __shfl_xor_sync(0xffffffffu, c, 2));                       // hadd
+    if ((lane & 3) == 0) pT[(size_t) j * ATT_QT + q_mine] = __fmul_rn(c, a.kq_scale);   // ggml_scale, PO.mm:617-621
+  }
+  __syncthreads();
+
+  // ---- soft_max (ggml.c:7019-7041): warp w owns query w; masked positions (diag_mask_inf) get probability 0 ----
+  {
+    const int qi = warp;
+    const int p_valid = qi < nq ? a.n_past + i0 + qi + 1 : 0;
+    float *col = pT + qi;
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < p_valid; j += 32) mx = fmaxf(mx, col[(size_t) j * ATT_QT]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double sum = 0.0;        // fp16-valued terms: the double sum is exact in any order
+    for (int j = lane; j < p_valid; j += 32) {
+      const uint16_t hx = __half_as_ushort(__float2half_rn(__fsub_rn(col[(size_t) j * ATT_QT], mx)));
+      const float e = __half2float(__ushort_as_half(a.exp_table[hx]));
+      col[(size_t) j * ATT_QT] = e;
+      sum += (double) e;
+    }
+    sum = warp_sum_d(sum);
+    const float inv = (float) (1.0 / sum);
+    for (int j = lane; j < pmax; j += 32)
+      col[(size_t) j * ATT_QT] = j < p_valid ? __fmul_rn(col[(size_t) j * ATT_QT], inv) : 0.0f;   // ggml_vec_scale_f32, ggml.c:7041
+  }
+  __syncthreads();
+
+  // ---- V.P: thread = (output dim d, query group qg of 4); reference thread t owns columns [t*dc, (t+1)*dc), FINALIZE adds
+  // the nth buffers in order (ggml.c:5570-5574) ----
+  {
+    const int d = tid & (HD - 1), qg = tid >> 7;
+    const int nth = a.n_threads;
+    const int dc = (p_part + nth - 1) / nth;
+    const float *vp = a.v_layer + h * HD + d;
+    float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int t = 0; t < nth; t++) {
+      const int j0 = t * dc;
+      const int j1 = min(min(j0 + dc, p_part), pmax);
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int j = j0;
+      for (; j + 8 <= j1; j += 8) {
+        float vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) vv[u] = vp[(size_t) (j + u) * E];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const float4 p4 = *reinterpret_cast<const float4 *>(pT + (size_t) (j + u) * ATT_QT + 4 * qg);
+          acc[0] = fmaf(vv[u], p4.x, acc[0]);                                   // ggml_vec_mad_f32, ggml.c:1696
+          acc[1] = fmaf(vv[u], p4.y, acc[1]);
+          acc[2] = fmaf(vv[u], p4.z, acc[2]);
+          acc[3] = fmaf(vv[u], p4.w, acc[3]);
+        }
+      }
+      for (; j < j1; j++) {
+        const float v = vp[(size_t) j * E];
+        const float4 p4 = *reinterpret_cast<const float4 *>(pT + (size_t) j * ATT_QT + 4 * qg);
+        acc[0] = fmaf(v, p4.x, acc[0]); acc[1] = fmaf(v, p4.y, acc[1]); acc[2] = fmaf(v, p4.z, acc[2]); acc[3] = fmaf(v, p4.w, acc[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = t == 0 ? acc[k] : __fadd_rn(o[k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (4 * qg + k < nq) a.out[(size_t) (i0 + 4 * qg + k) * E + h * HD + d] = o[k];      // KQV_merged, PO.mm:641-646
   }
 }
 

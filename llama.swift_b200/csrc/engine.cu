@@ -224,6 +224,7 @@ cudaError_t configure_kernels() {
   if ((e = cudaFuncSetAttribute(q4_gemm_cols_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(batch_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(q4_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(batch_attn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
@@ -281,6 +282,7 @@ struct b200_llama {
   size_t logits_log_cap = 0;
   int log_cap = 0;
   float *h_logits = nullptr;        // pinned
+  unsigned int *h_abort = nullptr;  // pinned copy of the device abort word (ptx.cuh: bounded waits)
   float kq_scale = 0.f;
   long long weight_bytes = 0;
   long long last_launches = 0;
@@ -306,6 +308,8 @@ struct b200_llama {
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
   int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1, opt_batch = 1, opt_tc = 1;
+  int opt_attn_tile = 1;                   // batches: query-tiled attention kernel (batch.cuh)
+  int opt_spin_limit = 0;                  // != 0: overrides the wait budget of the token kernel (clock ticks)
   bool want_tc_copy = false;               // keep a second copy of the weights in the prefill (tcgen05) layout
   __half *b_xh = nullptr;                  // [cap_pad][max K] fp16 quantized activations (tcgen05 operand source)
   float *b_dxT = nullptr;                  // [max nb][cap_pad] their block scales, transposed
@@ -321,6 +325,7 @@ struct b200_llama {
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
   const void *graph_log = nullptr, *graph_forced = nullptr;   // buffers baked into the captured kernel parameters
+  int graph_spin = 0;
 };
 
 namespace {
@@ -373,7 +378,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.epoch = m->d_epoch;
   // a spin-wait that outlives this many clock ticks traps instead of hanging the GPU; a multi-GPU group has to
   // tolerate the launch skew of its processes (graph instantiation, a slow host)
-  a.spin_limit = m->tp_size > 1 ? 40000000000LL : 4000000000LL;
+  a.spin_limit = m->opt_spin_limit ? (long long) m->opt_spin_limit : (m->tp_size > 1 ? 40000000000LL : 4000000000LL);
   a.bar = m->d_bar; a.n_embd = m->n_embd; a.n_head = m->n_head; a.n_ctx = m->n_ctx; a.n_ff = m->n_ff;
   a.n_threads = n_threads; a.kq_scale = m->kq_scale; a.S = m->mega_S; a.stage_bytes = m->mega_stage_bytes;
   a.xs_floats = m->mega_xs_floats;
@@ -462,7 +467,7 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
   const bool pdl = m->opt_pdl != 0;
   if (!m->opt_graph) return enqueue_token(m, n_threads, pdl, launches);
   const int key_pdl = (int) pdl | (mega_usable(m, n_threads) ? 2 : 0) | (m->fold_argmax ? 4 : 0);
-  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != key_pdl ||
+  if (!m->graph_exec || m->graph_threads != n_threads || m->graph_pdl != key_pdl || m->graph_spin != m->opt_spin_limit ||
       (m->fold_argmax && (m->graph_log != m->d_token_log || m->graph_forced != m->d_forced))) {
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
@@ -479,6 +484,7 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
     m->graph_threads = n_threads;
     m->graph_pdl = key_pdl;
     m->graph_log = m->d_token_log; m->graph_forced = m->d_forced;
+    m->graph_spin = m->opt_spin_limit;
   }
   if (launches) *launches += mega_usable(m, n_threads) ? 1 : 2 + 5LL * m->n_layer;
   return cudaGraphLaunch(m->graph_exec, m->stream);
@@ -821,7 +827,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   }
   CUDA_TRY(cudaMalloc(&m->d_sp, sizeof(StepParams)));
   CUDA_TRY(cudaMemset(m->d_sp, 0, sizeof(StepParams)));
-  CUDA_TRY(cudaMallocHost(&m->h_logits, (size_t) V * 4));
+  CUDA_TRY(cudaMallocHost(&m->h_logits, (size_t) V * 4 + 64));    // + the abort word read back with every call
+  m->h_abort = reinterpret_cast<unsigned int *>(m->h_logits + V);
+  *m->h_abort = 0;
   CUDA_TRY(configure_kernels());
   {
     std::vector<LayerDesc> descs(m->n_layer);
@@ -965,6 +973,31 @@ static std::vector<b200_llama *> ranks_of(b200_llama *m) {
 }
 
 
+
+// ---- bounded waits, host side (ptx.cuh): a device wait that gave up set the per-device abort word and the kernels ran to
+// completion on garbage.  Every entry point reads the word back with its results; when it is set the call fails with -1001,
+// and the exchange state (flag words, arrival counters, launch counter) is reset so that the NEXT call starts clean -- the
+// CUDA context stays healthy (the reference's failure path is an NSError from llama_eval, PO.mm:841-846).
+cudaError_t abort_fetch_async(b200_llama *m) {
+  return cudaMemcpyFromSymbolAsync(m->h_abort, g_b200_abort, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, m->stream);
+}
+
+bool abort_check_and_reset(const std::vector<b200_llama *> &ranks) {
+  bool aborted = false;
+  for (b200_llama *r : ranks) aborted = aborted || (r->h_abort && *r->h_abort != 0);
+  if (!aborted) return false;
+  for (b200_llama *r : ranks) {
+    cudaSetDevice(r->device);
+    const unsigned int zero = 0, one = 1;
+    cudaMemcpyToSymbol(g_b200_abort, &zero, sizeof(zero));
+    cudaMemset(r->d_xchg, 0, r->xchg_bytes);
+    cudaMemcpy(r->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice);
+    cudaMemset(r->d_bar, 0, 2 * sizeof(unsigned int));
+    *r->h_abort = 0;
+  }
+  return true;
+}
+
 // ---- prompt batches (batch.cuh) ------------------------------------------------------------------------------------------
 constexpr int kBatchChunk = 256;      // tokens evaluated together (bounds the activation buffers: ~210 KB per token at 7B)
 
@@ -989,9 +1022,9 @@ cudaError_t batch_reserve(b200_llama *m, int n) {
   if ((e = cudaMalloc(&m->b_act, (size_t) n * batch_act_bytes((int) (std::max(E, F) / 32)))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&m->b_tok, (size_t) n * 4)) != cudaSuccess) return e;
   if (m->want_tc_copy) {
-    const size_t npad = ((size_t) n + TC_T - 1) / TC_T * TC_T;
-    if ((e = cudaMalloc(&m->b_xh, npad * std::max(E, F) * 2)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&m->b_dxT, npad * (std::max(E, F) / 32) * 4)) != cudaSuccess) return e;
+    const size_t npad = ((size_t) n + TC_T - 1) / TC_T * TC_T, nbq = (std::max(E, F) / 32 + 3) / 4;
+    if ((e = cudaMalloc(&m->b_xh, npad / TC_T * nbq * TC_XH_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&m->b_dxT, npad / TC_T * nbq * TC_DX_BYTES)) != cudaSuccess) return e;
   }
   m->batch_cap = n;
   return cudaSuccess;
@@ -1003,7 +1036,7 @@ cudaError_t launch_gemm_cols(b200_llama *m, const GemvPlan &p, int n, float *out
 // persistent tcgen05 / TMEM kernel over (128-row tile, 16-token tile) items
 cudaError_t launch_gemm_tc(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches) {
   const int npad = (n + TC_T - 1) / TC_T * TC_T;
-  batch_act_tc_kernel<<<dim3((p.nb + 63) / 64, npad), 64, 0, m->stream>>>(m->b_act, batch_act_bytes(p.nb), m->b_xh, m->b_dxT, p.nb, n, npad);
+  batch_act_tc_kernel<<<dim3((((p.nb + 3) & ~3) + 63) / 64, npad), 64, 0, m->stream>>>(m->b_act, batch_act_bytes(p.nb), m->b_xh, m->b_dxT, p.nb, n, npad);
   GemmTcArgs a = {};
   a.w = p.d_wtc; a.M = p.M; a.nb = p.nb; a.xh = m->b_xh; a.dxT = m->b_dxT; a.out = out; a.ld_out = ld_out; a.N = n; a.Npad = npad;
   a.spin_limit = 4000000000LL;
@@ -1066,8 +1099,12 @@ cudaError_t enqueue_batch_chunk(b200_llama *m, int n_threads, int n_past_call, i
       BatchAttnArgs a = {};
       a.q = m->b_q; a.k_layer = k_layer; a.v_layer = v_layer; a.out = m->b_att; a.exp_table = m->d_exp;
       a.n_embd = E; a.n_threads = n_threads; a.n_ctx = m->n_ctx; a.n_past = n_past; a.N = n_past_call + n_call - n_past;
-      a.kq_scale = m->kq_scale;
-      batch_attn_kernel<<<dim3(m->n_head * ATTN_CLUSTER, n), ATTN_THREADS, attn_smem_bytes(m, n_threads), st>>>(a);   // PO.mm:614-646
+      a.kq_scale = m->kq_scale; a.N_chunk = n;
+      const size_t tile_smem = att_tile_smem(m->n_ctx);
+      if (m->opt_attn_tile && n >= 2 && tile_smem <= (size_t) kSmemBudget)     // 8 queries share every K / V row they read
+        batch_attn_tile_kernel<<<dim3(m->n_head, (n + ATT_QT - 1) / ATT_QT), ATT_TILE_THREADS, tile_smem, st>>>(a);
+      else
+        batch_attn_kernel<<<dim3(m->n_head * ATTN_CLUSTER, n), ATTN_THREADS, attn_smem_bytes(m, n_threads), st>>>(a);   // PO.mm:614-646
     }
     batch_prep_kernel<0><<<n, 256, 0, st>>>(m->b_att, nullptr, m->b_act, E);
     if ((e = launch_gemm_batch(m, L.wo, n, m->b_o, E, &nl)) != cudaSuccess) return e;                // PO.mm:649-651
@@ -1130,7 +1167,9 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
       CUDA_TRY(enqueue_batch_chunk(m, n_threads, n_past, n_tokens, t0, n, tokens, t0 + n == n_tokens, &m->last_launches));
     }
     CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(abort_fetch_async(m));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the evaluation was abandoned and the exchange state reset"); return fail_code; }
     memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
     return B200_LLAMA_OK;
   }
@@ -1149,11 +1188,13 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
     CUDA_TRY(cudaMemcpyAsync(r->h_logits, r->d_logits, (size_t) r->n_vocab * 4, cudaMemcpyDeviceToHost, r->stream));
+    CUDA_TRY(abort_fetch_async(r));
   }
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
   }
+  if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the evaluation was abandoned and the exchange state reset"); return fail_code; }
   memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);      // every rank holds the full logits; the leader's are returned
   return B200_LLAMA_OK;
 }
@@ -1254,11 +1295,13 @@ int b200_llama_decode_device(b200_llama *m, int n_threads, int n_past, int first
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
     CUDA_TRY(cudaEventRecord(r->ev1, r->stream));
+    CUDA_TRY(abort_fetch_async(r));
   }
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
   }
+  if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the run was abandoned and the exchange state reset"); return fail_code; }
   CUDA_TRY(cudaSetDevice(m->device));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, m->ev0, m->ev1));
   if (m->opt_time_kernel) {
@@ -1459,6 +1502,8 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "fold_argmax")) { m->opt_fold = value; return 0; }
   if (!strcmp(key, "batch")) { m->opt_batch = value; return 0; }
   if (!strcmp(key, "tc")) { m->opt_tc = value; return 0; }
+  if (!strcmp(key, "attn_tile")) { m->opt_attn_tile = value; return 0; }
+  if (!strcmp(key, "spin_limit_cycles")) { m->opt_spin_limit = value; return 0; }    // test hook: provoke the bounded-wait abort path
   return -1;
 }
 

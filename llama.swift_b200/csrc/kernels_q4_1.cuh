@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
       const uint8_t *wbase = a.w + (size_t) rp.row0 * nb * 24;
       for (int k = 0; k < nchunks; k++) {
         const int s = k % S;
-        if (k >= S) mbar_wait(&empty[s], ((k / S) - 1) & 1);
+        if (k >= S && !mbar_wait(&empty[s], ((k / S) - 1) & 1)) return;
         const int cbk = min(a.cb, nb - k * a.cb);
         const uint32_t bytes = (uint32_t) cbk * R * 24;
         mbar_arrive_expect_tx(&full[s], bytes);

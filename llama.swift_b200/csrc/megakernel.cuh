@@ -98,7 +98,7 @@ struct TokenArgs {
   float *q;                 // roped Q of this token [n_embd] (rank-local: only this rank's heads are used)
   TpArgs tp;
   unsigned int *epoch;      // launch counter in HBM (>= 1): makes every flag value of every token unique
-  long long spin_limit;     // clock64 ticks before a spin-wait traps instead of hanging the box
+  long long spin_limit;     // clock64 ticks before a spin-wait gives up (sets the abort word, ptx.cuh) instead of hanging the box
   const double2 *rope;
   const uint16_t *silu_table, *exp_table;
   StepParams *sp;           // read at kernel start; advanced by the folded arg-max (below) at the very end
@@ -166,7 +166,7 @@ __device__ __forceinline__ float ll_wait1(const uint2 *p, uint32_t seq, long lon
     do {
       __nanosleep(20);
       r = ld_vol_v2(p);
-      if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+      if (wait_give_up(t0, limit)) break;                      // never hang the box (ptx.cuh: bounded waits)
     } while (r.y != seq);
   }
   return __uint_as_float(r.x);
@@ -193,7 +193,7 @@ __device__ __forceinline__ void hint_wait(const unsigned int *cnt, unsigned int 
       const long long t0 = clock64();
       while ((int) (ld_vol_u32(cnt) - expected) < 0) {
         __nanosleep(40);
-        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+        if (wait_give_up(t0, limit)) break;                      // never hang the box
       }
     }
   }
@@ -225,7 +225,7 @@ __device__ __forceinline__ void plain_wait(const unsigned int *cnt, unsigned int
       const long long t0 = clock64();
       while ((int) ((sys ? ld_acquire_sys_u32(cnt) : ld_acquire_u32(cnt)) - expected) < 0) {
         __nanosleep(20);
-        if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+        if (wait_give_up(t0, limit)) break;                      // never hang the box
       }
     }
   }
@@ -351,7 +351,7 @@ __device__ __forceinline__ void ll_read_rounds(const uint2 *src, int items, int 
         const long long t0 = clock64();
         do {
           r[rd][i] = ld_vol_v4(p + i);
-          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+          if (wait_give_up(t0, limit)) break;                      // never hang the box
         } while (r[rd][i].y != seq || r[rd][i].w != seq);
       }
       v[rd][2 * i] = __uint_as_float(r[rd][i].x);
@@ -392,7 +392,7 @@ __device__ __forceinline__ void ll_read_rounds_staged(const uint2 *stage, const 
         const long long t0 = clock64();
         do {
           r = ld_vol_v4(pg + i);
-          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+          if (wait_give_up(t0, limit)) break;                      // never hang the box
         } while (r.y != seq || r.w != seq);
       }
       v[rd][2 * i] = __uint_as_float(r.x);
@@ -691,7 +691,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
         do {
           __nanosleep(20);
           w[i] = ld_vol_v2(src[i]);
-          if (clock64() - t0 > limit) { asm volatile("trap;"); }   // never hang the box
+          if (wait_give_up(t0, limit)) break;                      // never hang the box
         } while (w[i].y != seq);
       }
       sm.qkc[i < 8 ? (i < 4 ? 0 : 128) + lane + 32 * (i & 3) : 256 + lane] = __uint_as_float(w[i].x);
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
 #if B200_IDLE_PREFETCH
           if (!mbar_try_wait(&sm.empty[s], g.par ^ 1u)) prefetch_while_blocked(g.g);
 #endif
-          mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit);   // the consumers may be waiting for another GPU
+          if (!mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit)) return;   // (the consumers may be waiting for another GPU); abandoned: stop streaming
           const int cqk = min(cq, nbq - k * cq);
           const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
           mbar_arrive_expect_tx(&sm.full[s], bytes);
@@ -1181,7 +1181,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
             unsigned int v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tp.done[rank] + q) : "memory");
             if ((int) (v - epoch) >= 0) break;
-            if (clock64() - t0 > limit) { asm volatile("trap;"); }
+            if (wait_give_up(t0, limit)) break;
           }
         }
         *a.epoch = epoch + 1u;

@@ -18,11 +18,13 @@
 //
 // CTA = one 128-row weight tile x one 16-token tile at a time (persistent over a tile list, token tiles fastest so that the
 // CTAs working at the same time share the weight tile through L2).  Warp roles:
-//     warps 0-3  epilogue: thread = weight row = TMEM lane; 16 tokens x 8 lanes of f32 accumulators live in registers
-//     warp 4     TMA producer: raw weight quads (4 blocks x 128 rows x 20 B = ONE cp.async.bulk of 10 KB) + the tokens' block scales
-//     warp 5     MMA issuer (one elected lane; owns the TMEM allocation)
-//     warp 6     B builder: writes the 4 non-zero fp16 of every (token, lane) column; the zero pattern is written once
-//     warps 7-10 A unpacker: 16 nibble bytes -> 32 fp16 per row per block, straight into the UMMA canonical layout
+//     warps 0-15  epilogue: thread = weight row = TMEM lane (four warps per lane quarter, 4 tokens each: one tcgen05.ld of 32
+//                 columns per block step and warp); 4 tokens x 8 lanes of f32 accumulators live in registers
+//     warp 16     TMA producer: per (item, quad of blocks) THREE cp.async.bulk boxes -- 10 KB of raw weights (4 blocks x 128
+//                 rows x 20 B), 4 KB of fp16 activations (16 tokens x 4 blocks), 256 B of block scales
+//     warp 17     MMA issuer (one elected lane; owns the TMEM allocation)
+//     warp 18     B builder: writes the 4 non-zero fp16 of every (token, lane) column; the zero pattern is written once
+//     warps 19-22 A unpacker: 16 nibble bytes -> 32 fp16 per row per block, straight into the UMMA canonical layout
 // Pipelines: raw ring (TMA <-> unpack/epilogue), operand buffers (unpack/build <-> MMA via tcgen05.commit), TMEM
 // accumulators (MMA <-> epilogue).  All mbarrier based; no __syncthreads in steady state.
 #pragma once
@@ -35,13 +37,16 @@ namespace b200 {
 constexpr int TC_M = 128;                 // weight rows per tile = UMMA M = TMEM lanes
 constexpr int TC_T = 16;                  // tokens per tile
 constexpr int TC_N = TC_T * 8;            // UMMA N: (token, lane) columns
-constexpr int TC_THREADS = 352;           // 11 warps
+constexpr int TC_EPI_WARPS = 16;          // epilogue warps: 4 per TMEM lane quarter, 4 tokens each
+constexpr int TC_THREADS = (TC_EPI_WARPS + 7) * 32;   // + TMA, MMA, B builder, 4 unpack warps
 constexpr int TC_RAW_STAGES = 3;
 constexpr int TC_QUAD_BYTES = TC_M * 80;  // 4 blocks x 128 rows x 20 B
 constexpr int TC_A_BYTES = TC_M * 64;     // 128 rows x 32 fp16
 constexpr int TC_B_BYTES = TC_N * 64;     // 128 columns x 32 fp16
 constexpr int TC_DX_BYTES = 4 * TC_T * 4; // block scales of the 16 tokens, 4 blocks
-constexpr int TC_SMEM = TC_RAW_STAGES * (TC_QUAD_BYTES + TC_DX_BYTES) + 2 * TC_A_BYTES + 2 * TC_B_BYTES + 256;
+constexpr int TC_XH_BYTES = TC_T * 4 * 64; // fp16 activations of the 16 tokens, 4 blocks
+constexpr int TC_STAGE_BYTES = TC_QUAD_BYTES + TC_XH_BYTES + TC_DX_BYTES;
+constexpr int TC_SMEM = TC_RAW_STAGES * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES + 256;
 
 // ---- prefill weight layout: [row tile mt][quad q] -> { [block b < 4][row r < 128][16 raw nibble bytes] | [row][4] f32 d } ---------
 __host__ __device__ __forceinline__ size_t tc_weight_bytes(int M, int nb) {
@@ -69,18 +74,22 @@ __global__ void repack_prefill_kernel(const uint8_t *src, uint8_t *dst, int M, i
   }
 }
 
-// ---- activation operand: fp16 copy of the quantized activations + transposed block scales ----------------------------------------
-// from batch_prep_kernel's planes (act): xh [Npad][K] half (values -7..7; rows >= N are zero), dxT [nb][Npad] float
-__global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __half *xh, float *dxT, int nb, int N, int Npad) {
+// ---- activation operand: fp16 copy of the quantized activations + block scales, one contiguous box per (token tile, quad) ----
+// from batch_prep_kernel's planes (act):
+//   xh  [token tile nt][quad q][token t < 16][block b < 4][32] half   (values -7..7; tokens >= N and blocks >= nb are zero)
+//   dxq [token tile nt][quad q][block b < 4][token t < 16]     float
+__global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __half *xh, float *dxq, int nb, int N, int Npad) {
   const int n = blockIdx.y;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  const int nbp = (nb + 3) & ~3;
-  __half2 *dst = reinterpret_cast<__half2 *>(xh + ((size_t) n * nb + b) * 32);
-  if (n >= N) {
+  const int nbq = (nb + 3) >> 2, nbp = nbq * 4;
+  if (b >= nbp) return;
+  const int nt = n / TC_T, t = n % TC_T, q = b >> 2, bq = b & 3;
+  __half2 *dst = reinterpret_cast<__half2 *>(xh + ((((size_t) nt * nbq + q) * TC_T + t) * 4 + bq) * 32);
+  float *dd = dxq + (((size_t) nt * nbq + q) * 4 + bq) * TC_T + t;
+  if (n >= N || b >= nb) {
 #pragma unroll
     for (int i = 0; i < 16; i++) dst[i] = __floats2half2_rn(0.0f, 0.0f);
-    dxT[(size_t) b * Npad + n] = 0.0f;
+    *dd = 0.0f;
     return;
   }
   const uint2 *xq = reinterpret_cast<const uint2 *>(act + (size_t) n * act_stride);
@@ -99,7 +108,7 @@ __global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __hal
       dst[8 + l] = __floats2half2_rn((float) e2, (float) e3);        // elements 16+2l, 17+2l
     }
   }
-  dxT[(size_t) b * Npad + n] = dxs[b];
+  *dd = dxs[b];
 }
 
 // ---- tcgen05 / TMEM wrappers ----------------------------------------------------------------------------------------------------
@@ -155,8 +164,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct GemmTcArgs {
   const uint8_t *w;        // prefill weight layout (repack_prefill_kernel)
   int M, nb;
-  const __half *xh;        // [Npad][nb*32] fp16 quantized activations
-  const float *dxT;        // [nb][Npad] block scales
+  const __half *xh;        // [nt][q][16 tokens][4 blocks][32] fp16 quantized activations
+  const float *dxT;        // [nt][q][4 blocks][16 tokens] block scales
   float *out;              // [N][ld_out]
   int ld_out, N, Npad;
   long long spin_limit;
@@ -170,56 +179,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
   const int n_mt = (a.M + TC_M - 1) / TC_M, n_nt = a.Npad / TC_T;
   const int n_items = n_mt * n_nt;
 
-  uint8_t *raw = smem;                                                       // [TC_RAW_STAGES][quad | dx]
-  constexpr int RAW_STRIDE = TC_QUAD_BYTES + TC_DX_BYTES;
-  uint8_t *abuf = smem + TC_RAW_STAGES * RAW_STRIDE;                          // [2][TC_A_BYTES]
+  uint8_t *raw = smem;                                                       // [TC_RAW_STAGES][weights quad | xh | dx]
+  uint8_t *abuf = smem + TC_RAW_STAGES * TC_STAGE_BYTES;                      // [2][TC_A_BYTES]
   uint8_t *bbuf = abuf + 2 * TC_A_BYTES;                                      // [2][TC_B_BYTES]
   uint64_t *bars = reinterpret_cast<uint64_t *>(bbuf + 2 * TC_B_BYTES);
-  uint64_t *raw_full = bars, *raw_empty = bars + TC_RAW_STAGES;               // TMA <-> unpack / epilogue
+  uint64_t *raw_full = bars, *raw_empty = bars + TC_RAW_STAGES;               // TMA <-> unpack / build / epilogue
   uint64_t *ab_full = bars + 2 * TC_RAW_STAGES, *ab_empty = ab_full + 2;      // unpack + build <-> MMA
   uint64_t *tm_full = ab_empty + 2, *tm_empty = tm_full + 2;                  // MMA <-> epilogue
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
 
   if (tid == 0) {
-    for (int s = 0; s < TC_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }   // 4 unpack + 4 epilogue warps
+    for (int s = 0; s < TC_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TC_EPI_WARPS + 5); }   // epilogue warps + B builder + 4 unpack warps
     for (int i = 0; i < 2; i++) {
       mbar_init(&ab_full[i], 5);       // 4 unpack warps + the B builder
       mbar_init(&ab_empty[i], 1);      // tcgen05.commit
       mbar_init(&tm_full[i], 1);       // tcgen05.commit
-      mbar_init(&tm_empty[i], 4);      // 4 epilogue warps
+      mbar_init(&tm_empty[i], TC_EPI_WARPS);   // the epilogue warps
     }
     fence_mbar_init();
   }
   // the zero pattern of the block-diagonal operand is written once; only the non-zero positions are rewritten per block
   for (int i = tid; i < 2 * TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(bbuf)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
-  if (warp == 5) tmem_alloc(tmem_slot, 256);      // 2 accumulator buffers of 128 columns
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, 256);      // 2 accumulator buffers of 128 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long limit = a.spin_limit;
 
-  if (warp == 4) {
-    // ===== TMA producer =====
+  if (warp == TC_EPI_WARPS) {
+    // ===== TMA producer: three boxes per (item, quad) -- 10 KB of weights, 4 KB of fp16 activations, 256 B of block scales =====
     if (lane == 0) {
       uint32_t g = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = item / n_nt, nt = item % n_nt;
         for (int q = 0; q < nbq; q++, g++) {
           const int s = g % TC_RAW_STAGES;
-          if (g >= TC_RAW_STAGES) mbar_wait(&raw_empty[s], ((g / TC_RAW_STAGES) - 1) & 1, limit);
-          uint8_t *dst = raw + (size_t) s * RAW_STRIDE;
-          mbar_arrive_expect_tx(&raw_full[s], TC_QUAD_BYTES + TC_DX_BYTES);
+          if (g >= TC_RAW_STAGES && !mbar_wait(&raw_empty[s], ((g / TC_RAW_STAGES) - 1) & 1, limit)) { item = n_items; break; }   // abandoned: stop issuing
+          uint8_t *dst = raw + (size_t) s * TC_STAGE_BYTES;
+          mbar_arrive_expect_tx(&raw_full[s], TC_STAGE_BYTES);
           tma_bulk_g2s(dst, a.w + ((size_t) mt * nbq + q) * TC_QUAD_BYTES, TC_QUAD_BYTES, &raw_full[s]);
-          for (int b = 0; b < 4; b++) {
-            const int kb = min(4 * q + b, a.nb - 1);      // blocks past the end: any valid scales (their weight scale is 0)
-            tma_bulk_g2s(dst + TC_QUAD_BYTES + b * TC_T * 4, a.dxT + (size_t) kb * a.Npad + nt * TC_T, TC_T * 4, &raw_full[s]);
-          }
+          tma_bulk_g2s(dst + TC_QUAD_BYTES, reinterpret_cast<const uint8_t *>(a.xh) + ((size_t) nt * nbq + q) * TC_XH_BYTES, TC_XH_BYTES, &raw_full[s]);
+          tma_bulk_g2s(dst + TC_QUAD_BYTES + TC_XH_BYTES, reinterpret_cast<const uint8_t *>(a.dxT) + ((size_t) nt * nbq + q) * TC_DX_BYTES, TC_DX_BYTES, &raw_full[s]);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = f16, both K-major, N = 128, M = 128
@@ -229,8 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
         for (int kb = 0; kb < nbq * 4; kb++, kb_g++) {
           const int buf = kb_g & 1;
           const uint32_t par = (kb_g >> 1) & 1;
-          mbar_wait(&ab_full[buf], par, limit);
-          if (kb_g >= 2) mbar_wait(&tm_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
+          if (!mbar_wait(&ab_full[buf], par, limit) || (kb_g >= 2 && !mbar_wait(&tm_empty[buf], ((kb_g >> 1) - 1) & 1, limit))) { item = n_items; break; }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(abuf + buf * TC_A_BYTES), b_addr = smem_u32(bbuf + buf * TC_B_BYTES);
           const uint32_t d_tmem = tmem_base + (uint32_t) buf * TC_N;
@@ -242,46 +247,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == TC_EPI_WARPS + 2) {
     // ===== B builder: column (t, l) of block kb gets token t's activations at elements 2l, 2l+1 (K chunk l/4) and 16+2l, 17+2l
-    // (K chunk 2 + l/4); every lane handles 4 (t, l) pairs =====
-    uint32_t kb_g = 0;
+    // (K chunk 2 + l/4), read from the staged fp16 copy; every lane handles 4 (t, l) pairs =====
+    uint32_t g = 0, kb_g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int nt = item % n_nt;
-      const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.xh);      // fp16 pairs
-      uint32_t v0[4], v1[4];
-      auto fetch = [&](int kb) {
-        const int kbc = min(kb, a.nb - 1);
+      for (int q = 0; q < nbq; q++, g++) {
+        const int s = g % TC_RAW_STAGES;
+        mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
+        const uint32_t *xs = reinterpret_cast<const uint32_t *>(raw + (size_t) s * TC_STAGE_BYTES + TC_QUAD_BYTES);   // [t][b][16 words]
+        for (int b = 0; b < 4; b++, kb_g++) {
+          const int buf = kb_g & 1;
+          uint32_t v0[4], v1[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int i = lane + 32 * j, t = i >> 3, l = i & 7;
-          const uint32_t *row = xw + ((size_t) (nt * TC_T + t) * a.nb + kbc) * 16;
-          const bool live = kb < a.nb;
-          v0[j] = live ? __ldg(row + l) : 0u;
-          v1[j] = live ? __ldg(row + 8 + l) : 0u;
-        }
-      };
-      fetch(0);
-      for (int kb = 0; kb < nbq * 4; kb++, kb_g++) {
-        const int buf = kb_g & 1;
-        if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
-        uint8_t *B = bbuf + buf * TC_B_BYTES;
+          for (int j = 0; j < 4; j++) {
+            const int i = lane + 32 * j, t = i >> 3, l = i & 7;
+            v0[j] = xs[(t * 4 + b) * 16 + l];
+            v1[j] = xs[(t * 4 + b) * 16 + 8 + l];
+          }
+          if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
+          uint8_t *B = bbuf + buf * TC_B_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int i = lane + 32 * j, t = i >> 3, l = i & 7;
-          uint8_t *p = B + (l >> 2) * (TC_N * 16) + t * 128 + l * 16 + 4 * (l & 3);
-          *reinterpret_cast<uint32_t *>(p) = v0[j];
-          *reinterpret_cast<uint32_t *>(p + 2 * TC_N * 16) = v1[j];
+          for (int j = 0; j < 4; j++) {
+            const int i = lane + 32 * j, t = i >> 3, l = i & 7;
+            uint8_t *p = B + (l >> 2) * (TC_N * 16) + t * 128 + l * 16 + 4 * (l & 3);
+            *reinterpret_cast<uint32_t *>(p) = v0[j];
+            *reinterpret_cast<uint32_t *>(p + 2 * TC_N * 16) = v1[j];
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ab_full[buf]);
         }
-        if (kb + 1 < nbq * 4) fetch(kb + 1);           // in flight under the next wait
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ab_full[buf]);
+        if (lane == 0) mbar_arrive(&raw_empty[s]);
       }
     }
-  } else if (warp >= 7) {
+  } else if (warp >= TC_EPI_WARPS + 3) {
     // ===== A unpacker: thread = weight row; 16 nibble bytes -> 32 fp16 (q - 8), chunk c = elements 8c..8c+7 = nibble word c =====
-    const int row = (warp - 7) * 32 + lane;
+    const int row = (warp - (TC_EPI_WARPS + 3)) * 32 + lane;
     uint32_t g = 0, kb_g = 0;
     const __half2 mulv = __halves2half2(__float2half(1.0f), __float2half(0.0625f));
     const __half2 addv = __halves2half2(__float2half(-1032.0f), __float2half(-72.0f));
@@ -289,13 +292,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
       for (int q = 0; q < nbq; q++, g++) {
         const int s = g % TC_RAW_STAGES;
         mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
-        const uint8_t *st = raw + (size_t) s * RAW_STRIDE;
+        const uint8_t *st = raw + (size_t) s * TC_STAGE_BYTES;
         for (int b = 0; b < 4; b++, kb_g++) {
           const int buf = kb_g & 1;
           const uint4 nib = *reinterpret_cast<const uint4 *>(st + (size_t) b * TC_M * 16 + row * 16);
-          if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
-          uint8_t *A = abuf + buf * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
           const uint32_t ww[4] = {nib.x, nib.y, nib.z, nib.w};
+          uint4 out4[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             uint32_t h[4];
@@ -308,8 +310,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
               const __half2 r = __hfma2(*reinterpret_cast<const __half2 *>(&t), mulv, addv);
               h[i] = *reinterpret_cast<const uint32_t *>(&r);
             }
-            *reinterpret_cast<uint4 *>(A + c * (TC_M * 16)) = make_uint4(h[0], h[1], h[2], h[3]);
+            out4[c] = make_uint4(h[0], h[1], h[2], h[3]);
           }
+          if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
+          uint8_t *A = abuf + buf * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+          for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(A + c * (TC_M * 16)) = out4[c];
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ab_full[buf]);
@@ -319,48 +325,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
       }
     }
   } else {
-    // ===== epilogue warps 0-3: thread = row = TMEM lane 32*warp + lane =====
-    const int row = warp * 32 + lane;
-    const uint32_t t_lane = ((uint32_t) (warp * 32)) << 16;
+    // ===== epilogue warps: thread = row = TMEM lane 32*(warp % 4) + lane; warp group (warp / 4) takes TH tokens.  Several
+    // warps per TMEM lane quarter, so the others compute while one waits for its tcgen05.ld =====
+    constexpr int TH = TC_T / (TC_EPI_WARPS / 4);          // tokens per warp: 4
+    static_assert(TH * 8 == 32, "one 32-column tcgen05.ld per block step and warp");
+    const int wq = warp & 3, tg = warp >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t t_lane = ((uint32_t) (wq * 32)) << 16;
     uint32_t g = 0, kb_g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / n_nt, nt = item % n_nt;
-      u64 acc[TC_T][4];
+      u64 acc[TH][4];
 #pragma unroll
-      for (int t = 0; t < TC_T; t++)
+      for (int t = 0; t < TH; t++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[t][j] = pack_f2(0.0f, 0.0f);
       for (int q = 0; q < nbq; q++, g++) {
         const int s = g % TC_RAW_STAGES;
         mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
-        const uint8_t *st = raw + (size_t) s * RAW_STRIDE;
+        const uint8_t *st = raw + (size_t) s * TC_STAGE_BYTES;
         const float4 dw4 = *reinterpret_cast<const float4 *>(st + (size_t) 4 * TC_M * 16 + row * 16);
         const float dw[4] = {dw4.x, dw4.y, dw4.z, dw4.w};
-        const float *dxq = reinterpret_cast<const float *>(st + TC_QUAD_BYTES);
+        const float *dxq = reinterpret_cast<const float *>(st + TC_QUAD_BYTES + TC_XH_BYTES) + tg * TH;
 #pragma unroll
         for (int b = 0; b < 4; b++, kb_g++) {
           const int buf = kb_g & 1;
+          const float4 dx4 = *reinterpret_cast<const float4 *>(dxq + b * TC_T);
+          const float dxv[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
           mbar_wait(&tm_full[buf], (kb_g >> 1) & 1, limit);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + t_lane + (uint32_t) buf * TC_N;
-#pragma unroll
-          for (int part = 0; part < 8; part++) {        // 16 columns = 2 tokens x 8 lanes at a time
-            uint32_t d[16];
-            tmem_ld16(taddr + part * 16, d);
-            tmem_ld_wait();
-#pragma unroll
-            for (int tt = 0; tt < 2; tt++) {
-              const int t = part * 2 + tt;
-              const float sdx = __fmul_rn(dw[b], dxq[b * TC_T + t]);                                   // _mm256_mul_ps(d0, d1), ggml.c:1431
-              const u64 s2 = pack_f2(sdx, sdx);
-#pragma unroll
-              for (int j = 0; j < 4; j++)
-                acc[t][j] = ffma2(s2, pack_i2((int) d[tt * 8 + 2 * j], (int) d[tt * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
-            }
-          }
+          uint32_t d[32];                                  // 32 columns = this warp's 4 tokens x 8 lanes
+          tmem_ld32(tmem_base + t_lane + (uint32_t) buf * TC_N + (uint32_t) tg * (TH * 8), d);
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tm_empty[buf]);
+          if (lane == 0) mbar_arrive(&tm_empty[buf]);      // the accumulator buffer is free as soon as it is in registers
+#pragma unroll
+          for (int t = 0; t < TH; t++) {
+            const float sdx = __fmul_rn(dw[b], dxv[t]);                                              // _mm256_mul_ps(d0, d1), ggml.c:1431
+            const u64 s2 = pack_f2(sdx, sdx);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              acc[t][j] = ffma2(s2, pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[s]);
@@ -368,13 +375,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
       // horizontal sum exactly as ggml.c:1461-1466: (acc[k] + acc[k+4]) k < 4, then (r0 + r2) + (r1 + r3)
       const int grow = mt * TC_M + row;
 #pragma unroll
-      for (int t = 0; t < TC_T; t++) {
+      for (int t = 0; t < TH; t++) {
         float l[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) unpack_f2(acc[t][j], l[2 * j], l[2 * j + 1]);
         const float r0 = __fadd_rn(l[4], l[0]), r1 = __fadd_rn(l[5], l[1]), r2 = __fadd_rn(l[6], l[2]), r3 = __fadd_rn(l[7], l[3]);
         const float res = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-        const int n = nt * TC_T + t;
+        const int n = nt * TC_T + tg * TH + t;
         if (grow < a.M && n < a.N) a.out[(size_t) n * a.ld_out + grow] = res;
       }
     }
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }

@@ -83,13 +83,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a lost arrival must never hang the GPU box -- trap after ~2 s instead.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, long long limit = 4000000000LL) {
-  if (mbar_try_wait(bar, parity)) return;
+// ---- bounded waits ----------------------------------------------------------------------------------------------------
+// A lost arrival must never hang the GPU box, and a `trap` would poison the CUDA context of the whole process.  Instead a
+// spin-wait that outlives its budget sets the per-device abort word and FALLS THROUGH: the kernel runs to completion on
+// garbage, so every barrier is still reached and every thread exits normally; any other wait that has already spun for
+// ~0.5 ms looks at the word and gives up too (a healthy wait is far shorter, so the word is never read in normal
+// operation).  The host reads the word after the launch, reports -1001 and resets the exchange state (engine.cu).
+__device__ unsigned int g_b200_abort;
+__device__ __forceinline__ bool wait_give_up(long long t0, long long limit) {
+  const long long dt = clock64() - t0;
+  if (dt > limit || (dt > 1000000LL && *reinterpret_cast<volatile unsigned int *>(&g_b200_abort) != 0u)) {
+    *reinterpret_cast<volatile unsigned int *>(&g_b200_abort) = 1u;
+    return true;
+  }
+  return false;
+}
+// returns false when the wait was abandoned.  CONSUMERS may ignore that (they go on with garbage and keep arriving once per
+// stage, so no barrier is over- or under-subscribed); a PRODUCER must stop issuing: re-arming a full barrier whose previous
+// phase never completed overflows its transaction count.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, long long limit = 4000000000LL) {
+  if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > limit) { asm volatile("trap;"); }
+    if (wait_give_up(t0, limit)) return false;
   }
+  return true;
 }
 // 1-D bulk async copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

@@ -313,3 +313,29 @@ def test_long_context_teacher_forced(oracle_lib, small_model, n_threads):
     finally:
         ora.free()
         gpu.free()
+
+
+def test_bounded_wait_abort_and_recover(oracle_lib, small_model):
+    """a device-side wait that times out must not poison the CUDA context.  With a 300-tick wait budget
+    the token kernel gives up (abort word, csrc/ptx.cuh), the call returns -1001 (the reference's predict error code,
+    LlamaError.h:18), the exchange state is reset, and the NEXT call is bit-identical to the oracle again."""
+    ora = CpuModel(oracle_lib, "ora", small_model, 64)
+    gpu = lsb.llama_model_load(small_model, n_ctx=64)
+    try:
+        toks = np.array([1, 17, 33, 250, 9], np.int32)
+        gpu.set_option("batch", 0)
+        want = ora.eval(8, 0, toks)
+        assert np.array_equal(bits(lsb.llama_eval(gpu, 8, 0, toks)), bits(want))
+        gpu.set_option("spin_limit_cycles", 300)
+        with pytest.raises(lsb.LlamaError) as ei:
+            for _ in range(4):      # some launch will have a wait longer than 300 ticks
+                lsb.llama_eval(gpu, 8, 0, toks)
+        assert ei.value.code == -1001
+        gpu.set_option("spin_limit_cycles", 0)
+        again = lsb.llama_eval(gpu, 8, 0, toks)
+        assert np.array_equal(bits(again), bits(want))
+        step = lsb.llama_eval(gpu, 8, 5, np.array([int(want.argmax())], np.int32))
+        assert np.array_equal(bits(step), bits(ora.eval(8, 5, np.array([int(want.argmax())], np.int32))))
+    finally:
+        ora.free()
+        gpu.free()
