@@ -226,12 +226,103 @@ def parity_block(model, lsb, ref, n_threads: int):
             "bit_identical_steps": bit, "tolerance": 1e-3, "ok": bool(got_first == ref["first"] and np.array_equal(gtoks, toks) and rel.max() <= 1e-3)}
 
 
+
+# ---- configs[2]: 2048-token prefill through the batch path -----------------------------------------------------------------------
+PREFILL_FLOP_PER_TOKEN = 2 * 6_607_077_376          # the 225 mat-muls; lm_head counted like the reference (all rows)
+
+
+def prefill_tokens(n):
+    return np.random.default_rng(1234).integers(3, 32000, size=n).astype(np.int32)
+
+
+def bench_prefill(args, steps, warmup):
+    import torch
+    import llama_swift_b200 as lsb
+    n = args.prompt_tokens
+    path = ensure_model(args.layers)
+    model = lsb.llama_model_load(path, n_ctx=n + 8, device=0)
+    toks = prefill_tokens(n)
+    # parity at a size the CPU reference evaluates in seconds: the first 64 tokens as ONE batched llama_eval call
+    parity = None
+    if not args.no_parity:
+        L = ref_lib()
+        if L is not None:
+            err = C.create_string_buffer(512)
+            h = L.ref_llama_load(path.encode(), 72, err, 512)
+            if h:
+                h = C.c_void_p(h)
+                want = np.empty(model.n_vocab, np.float32)
+                t64 = np.ascontiguousarray(toks[:64])
+                t0 = time.perf_counter()
+                L.ref_llama_eval(h, args.threads, 0, t64.ctypes.data, 64, want.ctypes.data, err, 512)
+                cpu_s = time.perf_counter() - t0
+                L.ref_llama_free(h)
+                got = lsb.llama_eval(model, args.threads, 0, t64)
+                rel = float(np.linalg.norm(got.astype(np.float64) - want) / max(np.linalg.norm(want.astype(np.float64)), 1e-30))
+                parity = {"prompt_tokens": 64, "vs": "oracle/_ref (unmodified reference llama_eval, one N = 64 call), %d threads" % args.threads,
+                          "argmax_equal": bool(int(got.argmax()) == int(want.argmax())), "max_rel_l2": rel,
+                          "bit_identical": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))), "tolerance": 1e-3,
+                          "ok": bool(rel <= 1e-3 and int(got.argmax()) == int(want.argmax())), "reference_cpu_tokens_per_s": 64 / cpu_s}
+    for _ in range(warmup):
+        lsb.llama_eval(model, args.threads, 0, toks)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    dev_ms, wall = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        lsb.llama_eval(model, args.threads, 0, toks)       # host token ids in, last token's logits out (pinned staging in the library)
+        wall.append(time.perf_counter() - t0)
+        dev_ms.append(model.last_eval_ms)
+    torch.cuda.synchronize()
+    clocks = sampler.summary()
+    launches = model.last_launches
+    ms = float(np.mean(dev_ms))
+    tps = n / (ms * 1e-3)
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = (float(json.load(open(peaks_file))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)") \
+        if os.path.exists(peaks_file) else (1400.0, "fallback (B200_PROFILING.md)")
+    flops = PREFILL_FLOP_PER_TOKEN * n + 2.0 * n * n * 4096 * 32        # + causal attention ~ 2 N^2 n_embd n_layer
+    achieved = flops / (ms * 1e-3) / 1e12
+    tc_prof = None
+    tpf = os.path.join(ROOT, "profiles", "r2_prefill_tc_ncu.json")
+    if os.path.exists(tpf):
+        tc_prof = json.load(open(tpf))
+    line = {"metric": "prefill tokens/sec LLaMA-7B Q4_0, %d-token prompt" % n, "value": tps, "unit": "tokens/s", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int4 x int4 block dots as exact fp16 x fp16 -> f32 tcgen05.mma (TMEM accumulators), fp32 lane accumulation (bit-exact AVX2 order), f32 KV",
+            "data": "synthetic",
+            "config": {"workload": "LLaMA-7B Q4_0 prefill, %d-token prompt in one llama_eval call (BASELINE.json configs[2])" % n,
+                       "model_file": "synthetic ggml-format 7B (n_embd 4096, n_layer %d, n_vocab 32000), seed 0" % args.layers,
+                       "n_ctx": n + 8, "chunking": "256-token chunks inside the library", "ref_threads_mirrored": args.threads,
+                       "l2_policy": "per-step working set (4.13 GB weights + activations) >> 126 MB L2, no flush needed", "parallelism": "1 GPU"},
+            "clocks": clocks,
+            "e2e": {"value": n / float(np.mean(wall)), "unit": "tokens/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(model.n_vocab * 4),
+                    "note": "b200_llama_eval wall time: token ids from host memory, logits back to host memory"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "q4_gemm_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "algorithmic flops = 2 x 6.607e9 per token + causal attention; the exact per-lane fp32 fma chain of Q4_0 x Q4_0 is drained from TMEM "
+                                 "after every 32-element block, which bounds the kernel (DESIGN.md section 4.4), not the tensor pipe",
+                         "ncu": tc_prof},
+            "cpu_baseline": None if parity is None else {"value": parity["reference_cpu_tokens_per_s"], "unit": "tokens/s", "cores": args.threads, "kind": "reference",
+                                                          "sample": "reference llama_eval of the first 64 prompt tokens in one call (N = 64), %d threads" % args.threads},
+            "parity": parity}
+    print(json.dumps(line))
+    model.free()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
+                    help="decode = BASELINE.json's metric (configs[1]); prefill = configs[2]: one llama_eval of a 2048-token prompt "
+                         "(batch path: tcgen05 / TMEM mat-mul), a step = one whole prompt")
+    ap.add_argument("--prompt-tokens", type=int, default=2048)
     ap.add_argument("--layers", type=int, default=32, help="debug: fewer layers (the result is then NOT the benchmark)")
     ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -255,6 +346,38 @@ def main():
     if args.layers != 32:
         config["workload"] += f" [DEBUG: {args.layers} layers -- not the benchmark]"
 
+    if args.impl == "reference" and args.mode == "prefill":
+        if rank != 0:
+            return 0
+        # bounded sample of the prefill workload: the first 64 prompt tokens as ONE batched reference llama_eval per step
+        path = ensure_model(args.layers)
+        L = ref_lib()
+        if L is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libllama_ref.so not available"}))
+            return 0
+        cores = os.cpu_count() or 1
+        nth = min(cores, 16)
+        err = C.create_string_buffer(512)
+        h = C.c_void_p(L.ref_llama_load(path.encode(), 72, err, 512))
+        t64 = np.ascontiguousarray(prefill_tokens(args.prompt_tokens)[:64])
+        out = np.empty(32000, np.float32)
+        times = []
+        for i in range(1 + max(1, min(steps, 5))):
+            t0 = time.perf_counter()
+            L.ref_llama_eval(h, nth, 0, t64.ctypes.data, 64, out.ctypes.data, err, 512)
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+        L.ref_llama_free(h)
+        tps = 64 / float(np.mean(times))
+        desc = "reference ggml CPU path (oracle/_ref), %d threads of %d host cores: llama_eval of a 64-token slice of the prompt in one call" % (nth, cores)
+        print(json.dumps({"impl": "reference", "metric": "prefill tokens/sec LLaMA-7B Q4_0, %d-token prompt" % args.prompt_tokens, "value": tps,
+                          "unit": "tokens/s", "n_gpus": n_gpus, "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * float(np.mean(times)),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int4 x int4 -> int32 block dots, fp32 accumulate (AVX2 CPU)",
+                          "data": "synthetic", "config": {"workload": "LLaMA-7B Q4_0 prefill (BASELINE.json configs[2]); CPU sample: 64 tokens per step"},
+                          "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": nth, "kind": "reference", "sample": desc},
+                          "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -271,6 +394,11 @@ def main():
                 "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
+
+    if args.mode == "prefill":
+        if rank != 0:
+            return 0
+        return bench_prefill(args, max(1, min(steps, 5)) if args.steps != 512 else 3, warmup)
 
     import torch
     import llama_swift_b200 as lsb

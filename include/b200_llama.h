@@ -157,6 +157,9 @@ long long b200_llama_weight_bytes(const b200_llama *m);
 /* With option "time_kernel" = 1, b200_llama_decode_device brackets every token-kernel launch with CUDA events on the
  * model's stream; this returns the sum of those per-launch durations (ms) for the last call. */
 double b200_llama_last_kernel_ms(const b200_llama *m);
+/* Device time (ms, CUDA events on the model's stream) of the last b200_llama_eval call that took the batch path
+ * (n_tokens > 1): embedding .. last token's logits, without the host copies. */
+double b200_llama_last_eval_ms(const b200_llama *m);
 int b200_llama_set_option(b200_llama *m, const char *key, int value);
 
 /* Development profiler of the whole-token kernel: evaluates one token at position pos and returns per-CTA

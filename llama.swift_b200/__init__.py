@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
     L.b200_llama_last_launches.argtypes, L.b200_llama_last_launches.restype = [vp], C.c_longlong
     L.b200_llama_weight_bytes.argtypes, L.b200_llama_weight_bytes.restype = [vp], C.c_longlong
     L.b200_llama_last_kernel_ms.argtypes, L.b200_llama_last_kernel_ms.restype = [vp], C.c_double
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_last_eval_ms"):
+        L.b200_llama_last_eval_ms.argtypes, L.b200_llama_last_eval_ms.restype = [vp], C.c_double
     L.b200_llama_set_option.argtypes, L.b200_llama_set_option.restype = [vp, cp, ci], ci
     L.b200_q4_0_matvec.argtypes = [ci, vp, ci, ci, vp, vp, ci, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_0_matvec.restype = ci
@@ -167,6 +169,11 @@ class LlamaModel:
     def kernel_ms_total(self) -> float:
         """Sum of the per-launch token-kernel durations of the last decode_device call (option time_kernel = 1)."""
         return float(lib().b200_llama_last_kernel_ms(self._h))
+
+    @property
+    def last_eval_ms(self) -> float:
+        """Device time (CUDA events) of the last batched llama_eval (n_tokens > 1)."""
+        return float(lib().b200_llama_last_eval_ms(self._h))
 
     @property
     def weight_bytes(self) -> int:

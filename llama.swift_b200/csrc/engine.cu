@@ -308,6 +308,7 @@ struct b200_llama {
   std::vector<b200_llama *> group;          // single-process group: the leader (rank 0) owns ranks 1..n-1
 
   int opt_graph = 1, opt_pdl = 0, opt_mega = 1, opt_time_kernel = 0, opt_fold = 1, opt_batch = 1, opt_tc = 1;
+  int tc_min_n = 24;                       // batches of at least this many tokens take the tcgen05 mat-mul
   int opt_attn_tile = 1;                   // batches: query-tiled attention kernel (batch.cuh)
   int opt_spin_limit = 0;                  // != 0: overrides the wait budget of the token kernel (clock ticks)
   bool want_tc_copy = false;               // keep a second copy of the weights in the prefill (tcgen05) layout
@@ -321,6 +322,7 @@ struct b200_llama {
   int fold_argmax = 0;                     // this launch folds the greedy pick into the token kernel (decode_device)
   float2 *d_am = nullptr;                  // per-CTA arg-max candidates
   double last_kernel_ms = 0.0;             // sum of per-launch token-kernel durations (opt_time_kernel)
+  double last_eval_ms = 0.0;               // device time of the last batched b200_llama_eval (CUDA events on the launching stream)
   std::vector<cudaEvent_t> kev;
   cudaGraphExec_t graph_exec = nullptr;   // one token step: embed .. logits
   int graph_threads = -1, graph_pdl = -1;
@@ -1048,7 +1050,9 @@ cudaError_t launch_gemm_tc(b200_llama *m, const GemvPlan &p, int n, float *out, 
 
 // tensor-core path for batches when the prefill copy exists; else the CUDA-core multi-column loop
 cudaError_t launch_gemm_batch(b200_llama *m, const GemvPlan &p, int n, float *out, int ld_out, long long *launches) {
-  if (m->opt_tc && p.d_wtc && m->b_xh && n >= 2) return launch_gemm_tc(m, p, n, out, ld_out, launches);
+  // measured on B200 (profiles/r2_e_to_i_prompt_batches.md): one 16-token tile costs ~13 ms for the whole 7B model on the tensor-core
+  // kernel (a 128-row tile walks its K loop alone), 8 columns ~5-9 ms on the CUDA-core loop: the crossover is near 20 tokens
+  if (m->opt_tc && p.d_wtc && m->b_xh && n >= m->tc_min_n) return launch_gemm_tc(m, p, n, out, ld_out, launches);
   return launch_gemm_cols(m, p, n, out, ld_out, launches);
 }
 
@@ -1162,13 +1166,16 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
     // prompt batch: every weight row is read once per group of columns (batch.cuh), not once per token
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(batch_reserve(m, std::min(n_tokens, kBatchChunk)));
+    CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
     for (int t0 = 0; t0 < n_tokens; t0 += kBatchChunk) {
       const int n = std::min(kBatchChunk, n_tokens - t0);
       CUDA_TRY(enqueue_batch_chunk(m, n_threads, n_past, n_tokens, t0, n, tokens, t0 + n == n_tokens, &m->last_launches));
     }
+    CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
     CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(abort_fetch_async(m));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_eval_ms = ms; }
     if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the evaluation was abandoned and the exchange state reset"); return fail_code; }
     memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
     return B200_LLAMA_OK;
@@ -1453,6 +1460,7 @@ int b200_llama_kv_import(b200_llama *m, int layer, int which, int n_rows, const 
 
 long long b200_llama_last_launches(const b200_llama *m) { return m->last_launches; }
 double b200_llama_last_kernel_ms(const b200_llama *m) { return m->last_kernel_ms; }
+double b200_llama_last_eval_ms(const b200_llama *m) { return m->last_eval_ms; }
 long long b200_llama_weight_bytes(const b200_llama *m) { return m->weight_bytes; }
 
 /* Development profiler: run ONE token (current step scalars) through the whole-token kernel with per-CTA globaltimer
@@ -1503,6 +1511,7 @@ int b200_llama_set_option(b200_llama *m, const char *key, int value) {
   if (!strcmp(key, "batch")) { m->opt_batch = value; return 0; }
   if (!strcmp(key, "tc")) { m->opt_tc = value; return 0; }
   if (!strcmp(key, "attn_tile")) { m->opt_attn_tile = value; return 0; }
+  if (!strcmp(key, "tc_min_n")) { m->tc_min_n = value; return 0; }
   if (!strcmp(key, "spin_limit_cycles")) { m->opt_spin_limit = value; return 0; }    // test hook: provoke the bounded-wait abort path
   return -1;
 }

@@ -18,6 +18,7 @@ def test_batch_vs_oracle(oracle_lib, small_model, n_threads, tc):
     ora = CpuModel(oracle_lib, "ora", small_model, 128)
     gpu = lsb.llama_model_load(small_model, n_ctx=128)
     gpu.set_option("tc", tc)
+    gpu.set_option("tc_min_n", 2)          # every batch size through the tensor-core kernel (the default switches at 24 tokens)
     try:
         rng = np.random.default_rng(23)
         n_past, exact, total = 0, 0, 0
