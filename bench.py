@@ -34,29 +34,55 @@ sys.path.insert(0, ROOT)
 PROMPT = [1, 15043, 3186, 29892, 590, 1024, 338, 29871]      # 8 fixed ids, BOS first (utils.cpp:284-286)
 N_PROMPT = len(PROMPT)
 
-# algorithmic bytes (BASELINE.md section 2 / SURVEY.md section 8d), LLaMA-7B Q4_0
-W_BYTES = 4_129_423_360
-S_BYTES = 1_064_960 + 2_560
-KV_ROW = 1_048_576            # 2 (K,V) * n_layer * n_embd * 4 B per cached position
+# algorithmic bytes (BASELINE.md section 2 / SURVEY.md section 8d), Q4_0: weights once (20 B per 32) + f32 norm weights + one
+# embedding row + f32 KV rows read / written
+MODELS = {"7b": dict(n_embd=4096, n_head=32, n_layer=32, n_ff=11008, n_vocab=32000),          # PO.mm:41-50
+          "13b": dict(n_embd=5120, n_head=40, n_layer=40, n_ff=13824, n_vocab=32000)}         # two-part file (PO.mm:35), BASELINE.json configs[3]
+MODEL = "7b"
 
 
-def algorithmic_bytes(pos: int) -> int:
-    return W_BYTES + S_BYTES + KV_ROW * (pos + 1) + KV_ROW
+def _geom(layers=None):
+    g = dict(MODELS[MODEL])
+    if layers:
+        g["n_layer"] = layers
+    return g
+
+
+def weight_bytes(layers=None) -> int:
+    g = _geom(layers)
+    e, f, v, l = g["n_embd"], g["n_ff"], g["n_vocab"], g["n_layer"]
+    return (l * (4 * e * e + 3 * e * f) + v * e) // 32 * 20
+
+
+W_BYTES = 4_129_423_360       # LLaMA-7B Q4_0 (== weight_bytes() for the default model)
+
+
+def algorithmic_bytes(pos: int, layers=None) -> int:
+    g = _geom(layers)
+    e, l = g["n_embd"], g["n_layer"]
+    s_bytes = (2 * l + 1) * e * 4 + e // 32 * 20
+    kv_row = 2 * l * e * 4            # K and V, f32, per cached position
+    return weight_bytes(layers) + s_bytes + kv_row * (pos + 1) + kv_row
 
 
 def model_path(layers: int) -> str:
     d = os.environ.get("B200_BENCH_DIR", "/tmp/b200_bench")
     os.makedirs(d, exist_ok=True)
-    return os.path.join(d, "ggml-model-q4_0.bin" if layers == 32 else f"ggml-model-q4_0-l{layers}.bin")
+    full = MODELS[MODEL]["n_layer"]
+    tag = "" if MODEL == "7b" else "-" + MODEL
+    return os.path.join(d, f"ggml-model{tag}-q4_0.bin" if layers == full else f"ggml-model{tag}-q4_0-l{layers}.bin")
 
 
 def ensure_model(layers: int) -> str:
     from llama_swift_b200 import ggml_format as gf
     path = model_path(layers)
-    if not os.path.exists(path):
+    n_parts = gf.LLAMA_N_PARTS[MODELS[MODEL]["n_embd"]]
+    if not all(os.path.exists(path if p == 0 else f"{path}.{p}") for p in range(n_parts)):
         tmp = path + f".tmp{os.getpid()}"
-        gf.write_synthetic_model(tmp, gf.HParams(n_layer=layers), seed=0, mode="direct")
-        os.replace(tmp, path)
+        g = MODELS[MODEL]
+        gf.write_synthetic_model(tmp, gf.HParams(n_vocab=g["n_vocab"], n_embd=g["n_embd"], n_head=g["n_head"], n_layer=layers), seed=0, mode="direct")
+        for p in range(n_parts):
+            os.replace(tmp + ("" if p == 0 else f".{p}"), path if p == 0 else f"{path}.{p}")
     return path
 
 
@@ -253,6 +279,9 @@ def bench_prefill(args, steps, warmup):
                 h = C.c_void_p(h)
                 want = np.empty(model.n_vocab, np.float32)
                 t64 = np.ascontiguousarray(toks[:64])
+                # the reference sizes its scratch buffer from the 4-token probe call it always makes first (PO.mm:822, 527-541)
+                probe = np.array([0, 1, 2, 3], np.int32)
+                L.ref_llama_eval(h, args.threads, 0, probe.ctypes.data, 4, want.ctypes.data, err, 512)
                 t0 = time.perf_counter()
                 L.ref_llama_eval(h, args.threads, 0, t64.ctypes.data, 64, want.ctypes.data, err, 512)
                 cpu_s = time.perf_counter() - t0
@@ -323,7 +352,8 @@ def main():
                     help="decode = BASELINE.json's metric (configs[1]); prefill = configs[2]: one llama_eval of a 2048-token prompt "
                          "(batch path: tcgen05 / TMEM mat-mul), a step = one whole prompt")
     ap.add_argument("--prompt-tokens", type=int, default=2048)
-    ap.add_argument("--layers", type=int, default=32, help="debug: fewer layers (the result is then NOT the benchmark)")
+    ap.add_argument("--model", default="7b", choices=sorted(MODELS), help="7b = BASELINE.json's metric; 13b = configs[3] (two-part file)")
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (the result is then NOT the benchmark)")
     ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the 24-step comparison with the reference CPU path")
@@ -331,6 +361,12 @@ def main():
                     help="N > 1: tp = ONE bs=1 generation over all GPUs (rows of every matrix split over the ranks; the metric "
                          "BASELINE.json names); replicas = N independent generations")
     args = ap.parse_args()
+    global MODEL
+    MODEL = args.model
+    full_layers = MODELS[MODEL]["n_layer"]
+    if not args.layers:
+        args.layers = full_layers
+    mname = "LLaMA-" + MODEL.upper()[:-1] + "B"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,12 +374,13 @@ def main():
     n_gpus = args.gpus
     steps, warmup = args.steps, max(3, args.warmup)
 
-    config = {"workload": "LLaMA-7B Q4_0 bs=1 decode, %d-token gen after an 8-token prompt%s" %
-                          (steps, " (BASELINE.json configs[1])" if steps == 512 else " (BASELINE.json configs[1] is the same with 512 tokens)"),
-              "model_file": "synthetic ggml-format 7B (n_embd 4096, n_layer %d, n_vocab 32000), seed 0" % args.layers,
+    config = {"workload": "%s Q4_0 bs=1 decode, %d-token gen after an 8-token prompt%s" %
+                          (mname, steps, (" (BASELINE.json configs[1])" if steps == 512 else " (BASELINE.json configs[1] is the same with 512 tokens)") if MODEL == "7b"
+                           else " (BASELINE.json configs[3])"),
+              "model_file": "synthetic ggml-format %s (n_embd %d, n_layer %d, n_vocab 32000), seed 0" % (MODEL.upper(), MODELS[MODEL]["n_embd"], args.layers),
               "n_past_start": N_PROMPT, "positions": [N_PROMPT, N_PROMPT + steps - 1], "ref_threads_mirrored": args.threads,
-              "l2_policy": "per-step working set (4.13 GB weights) >> 126 MB L2, no flush needed"}
-    if args.layers != 32:
+              "l2_policy": "per-step working set (%.2f GB weights) >> 126 MB L2, no flush needed" % (weight_bytes() / 1e9)}
+    if args.layers != full_layers:
         config["workload"] += f" [DEBUG: {args.layers} layers -- not the benchmark]"
 
     if args.impl == "reference" and args.mode == "prefill":
@@ -361,6 +398,8 @@ def main():
         h = C.c_void_p(L.ref_llama_load(path.encode(), 72, err, 512))
         t64 = np.ascontiguousarray(prefill_tokens(args.prompt_tokens)[:64])
         out = np.empty(32000, np.float32)
+        probe = np.array([0, 1, 2, 3], np.int32)      # sizes the reference's scratch buffer (PO.mm:822, 527-541)
+        L.ref_llama_eval(h, nth, 0, probe.ctypes.data, 4, out.ctypes.data, err, 512)
         times = []
         for i in range(1 + max(1, min(steps, 5))):
             t0 = time.perf_counter()
@@ -386,7 +425,7 @@ def main():
         if tps is None:
             print(json.dumps({"impl": "reference", "unavailable": desc}))
             return 0
-        line = {"impl": "reference", "metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s",
+        line = {"impl": "reference", "metric": "decode tokens/sec %s Q4_0 bs=1" % mname, "value": tps, "unit": "tokens/s",
                 "n_gpus": n_gpus, "steps": n, "warmup": 1, "ms_per_step": 1e3 / tps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int4 x int4 -> int32 block dots, fp32 accumulate (AVX2 CPU)",
                 "data": "synthetic", "config": config,
@@ -404,7 +443,13 @@ def main():
     import llama_swift_b200 as lsb
 
     dist = None
+    saved_stdout = None
     if world > 1:
+        # stdout carries exactly ONE JSON line: whatever the libraries print while the ranks talk to each other (NCCL's version
+        # banner, warnings) goes to stderr -- file descriptor 1 is pointed at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
@@ -503,7 +548,7 @@ def main():
 
     jobs = 1 if tp else world            # tp: ONE generation over all GPUs; replicas: one per GPU
     tps = jobs * steps / (ms_value * 1e-3)
-    mean_bytes = float(np.mean([algorithmic_bytes(N_PROMPT + i) for i in range(steps)])) if args.layers == 32 else None
+    mean_bytes = float(np.mean([algorithmic_bytes(N_PROMPT + i) for i in range(steps)])) if args.layers == full_layers else None
     if mean_bytes is not None and tp:
         mean_bytes /= world              # bytes one GPU streams per launch: its row shard of the weights, its heads' KV
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -516,7 +561,7 @@ def main():
     traffic, traffic_src = None, None
     for tf in ("r2_traffic.json", "r1_traffic.json"):
         tfp = os.path.join(ROOT, "profiles", tf)
-        if world == 1 and args.layers == 32 and os.path.exists(tfp):
+        if world == 1 and MODEL == "7b" and args.layers == full_layers and os.path.exists(tfp):
             traffic, traffic_src = json.load(open(tfp)).get("dram_bytes_per_launch"), "profiles/" + tf
             break
     roofline = None
@@ -524,7 +569,7 @@ def main():
         achieved = mean_bytes / (kernel_ms / steps * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "decode_token_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": mean_bytes, "weights_only_GBps": W_BYTES / (kernel_ms / steps * 1e-3) / 1e9,
+                    "algorithmic_bytes_per_launch": mean_bytes, "weights_only_GBps": weight_bytes() / (world if tp else 1) / (kernel_ms / steps * 1e-3) / 1e9,
                     "kernel_us_per_launch": kernel_ms / steps * 1e3}
 
     cpu = None
@@ -546,7 +591,7 @@ def main():
         par = f"{world} independent replicas" + (f" [{tp_note}]" if tp_note else "")
     config.update({"parallelism": par, "n_ctx": n_ctx,
                    "graph": "CUDA graph replay of [memset, decode_token_kernel] + argmax kernel per step"})
-    line = {"metric": "decode tokens/sec LLaMA-7B Q4_0 bs=1", "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": steps,
+    line = {"metric": "decode tokens/sec %s Q4_0 bs=1" % mname, "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_value / steps, "higher_is_better": True,
             "scaling": "weak" if (world > 1 and not tp) else "strong", "vs_baseline": None,
             "dtype": "int4 x int4 -> int32 block dots (dp4a), fp32 lane accumulation (bit-exact AVX2 order), f32 KV",
@@ -554,7 +599,12 @@ def main():
             "e2e": {"value": jobs * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
                     "note": "b200_llama_eval per token: token id by value, logits to pinned host memory, host arg-max"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    if saved_stdout is not None:
+        os.dup2(2, 1)
     model.free()
     if dist is not None:
         dist.destroy_process_group()

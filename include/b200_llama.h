@@ -170,6 +170,11 @@ int b200_llama_profile_token(b200_llama *m, int n_threads, int token, int pos, l
  * out[M] = W[M x K] (Q4_0, ggml row layout) * x[K] computed exactly as ggml_compute_forward_mul_mat_q4_0_f32 does. */
 int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out,
                      int lane_pairs, float *kernel_ms, char *err, size_t errlen);
+/* The same for N columns x[N][K] -> out[N][M] (the row-major mat-mul of a prompt batch, ggml.c:6199-6222): path 0 = CUDA-core
+ * multi-column loop (every weight row read once per 8 columns), path 1 = tcgen05 / TMEM kernel.  Every column is bit-identical
+ * to the single-column result.  kernel_ms (optional): best-of-5 device time of the mat-mul kernel alone. */
+int b200_q4_0_matmul(int device, const void *w_ggml, int M, int K, const float *x, int N, float *out, int path,
+                     float *kernel_ms, char *err, size_t errlen);
 
 /* Same for Q4_1 (ggml per-row layout [nb f32 min][nb f32 d][nb*16 B]): ggml_compute_forward_mul_mat_q4_1_f32,
  * ggml.c:6287-6585 (quantize_row_q4_1 ggml.c:606-648 + ggml_vec_dot_q4_1 ggml.c:1584-1626). */

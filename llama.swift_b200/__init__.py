@@ -95,6 +95,9 @@ def lib() -> C.CDLL:
     L.b200_llama_set_option.argtypes, L.b200_llama_set_option.restype = [vp, cp, ci], ci
     L.b200_q4_0_matvec.argtypes = [ci, vp, ci, ci, vp, vp, ci, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_0_matvec.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_q4_0_matmul"):
+        L.b200_q4_0_matmul.argtypes = [ci, vp, ci, ci, vp, ci, vp, ci, C.POINTER(C.c_float), cp, sz]
+        L.b200_q4_0_matmul.restype = ci
     L.b200_q4_1_matvec.argtypes = [ci, vp, ci, ci, vp, vp, C.POINTER(C.c_float), cp, sz]
     L.b200_q4_1_matvec.restype = ci
     if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_acquire"):
@@ -298,6 +301,22 @@ def q4_0_matvec(w_blocks: np.ndarray, x: np.ndarray, lane_pairs: int = 0, device
     ms = C.c_float(0)
     err = C.create_string_buffer(512)
     rc = lib().b200_q4_0_matvec(device, w.ctypes.data, M, K, x.ctypes.data, out.ctypes.data, lane_pairs,
+                                C.byref(ms) if timed else None, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return (out, ms.value) if timed else out
+
+
+def q4_0_matmul(w_blocks: np.ndarray, x: np.ndarray, path: int = 0, device: int = 0, timed: bool = False):
+    """out[N, M] = W x the N columns x[N, K] (kernel-level entry of the batch path; path 0 CUDA cores, 1 tcgen05)."""
+    w = np.ascontiguousarray(w_blocks, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    N, K = x.shape
+    M = w.size // (K // 32 * 20)
+    out = np.empty((N, M), dtype=np.float32)
+    ms = C.c_float(0)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_q4_0_matmul(device, w.ctypes.data, M, K, x.ctypes.data, N, out.ctypes.data, path,
                                 C.byref(ms) if timed else None, err, 512)
     if rc != 0:
         raise LlamaError(rc, err.value.decode(errors="replace"))

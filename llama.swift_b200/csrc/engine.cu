@@ -7,7 +7,10 @@
 //
 // There is deliberately no CPU fallback: every entry point fails with an error if CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -61,7 +64,7 @@ struct GemvPlan {
   uint8_t *d_w = nullptr;
   size_t bytes = 0;
   uint8_t *d_wtc = nullptr;   // the same weights in the tensor-core prefill layout (prefill_tc.cuh), or null
-  int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rpt = 1, rmax = 0, S = 0, stage_bytes = 0, threads = 0;
+  int M = 0, g_total = 0, nb = 0, n_cta = 0, cb = 0, lp = 0, rpt = 1, rmax = 0, S = 0, stage_bytes = 0, threads = 0, half_rows = 0;
   size_t smem = 0;
 };
 
@@ -114,6 +117,9 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   }
   p.lp = lp;
   p.threads = ((p.rmax * (4 / lp) + 31) & ~31) + 32;
+  // few-row matrices: the whole-token kernel walks the LP = 1 stream with EIGHT threads per row (megakernel.cuh:
+  // gemv_rows_half); encoded as half_rows = 1 on top of lp = 1 (the per-matrix kernels and the batch kernels use lp)
+  p.half_rows = (lp == 1 && rpt == 1 && p.rmax * 8 <= MEGA_COMPUTE_THREADS && env_int("B200_HALF_ROWS", 0) != 0) ? 1 : 0;   // measured on 1 GPU: no gain (1618 vs 1604 us/token), off by default
 #if B200_IMMA
   // Tensor-path row loop (rowloop_imma.cuh): lp = rows per warp tile (8 for few-row matrices, so that 4+ warps share the
   // work; else 16), rpt = tiles per warp (2 when a CTA owns more than 16 tiles).  lp_override 8 / 16 forces the tile.
@@ -247,10 +253,54 @@ cudaError_t launch_small(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// A tensor of the model file, referenced WHERE IT LIES in the memory-mapped part files (nothing is copied on the host until
+// its rows are staged for upload, and a tensor-parallel rank only ever touches the pages of its own row slices).
 struct HostTensor {
   int n_dims = 0, ftype = 0;
-  int ne[2] = {1, 1};
-  std::vector<uint8_t> data;
+  int ne[2] = {1, 1};              // merged shape (ne[0] = row length, ne[1] = rows)
+  int split = 1;                   // multi-part files: 0 = columns (ne[0]) split over the parts, 1 = rows (PO.mm:358-388)
+  int n_parts = 1;
+  const uint8_t *part[8] = {};     // start of this tensor's data in part p
+  size_t row_bytes = 0;            // bytes of one merged row (1-D tensors: the whole tensor)
+};
+
+// read-only mapping of one model part file
+struct FileMap {
+  const uint8_t *p = nullptr;
+  size_t size = 0;
+  ~FileMap() { if (p) munmap(const_cast<uint8_t *>(p), size); }
+  bool open_file(const char *path) {
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { ::close(fd); return false; }
+    void *q = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (q == MAP_FAILED) return false;
+    p = (const uint8_t *) q; size = (size_t) st.st_size;
+    madvise(q, size, MADV_WILLNEED);
+    return true;
+  }
+};
+
+// Two pinned staging buffers: the CPU assembles the next rows (merging the column slices of a multi-part file on the way)
+// while the previous buffer is in flight to the GPU.
+struct Stager {
+  static constexpr size_t kCap = 32u << 20;
+  uint8_t *buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int cur = 0;
+  cudaError_t init() {
+    for (int i = 0; i < 2; i++) {
+      cudaError_t e = cudaMallocHost(&buf[i], kCap);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  ~Stager() {
+    for (int i = 0; i < 2; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+  }
 };
 
 }  // namespace
@@ -339,7 +389,7 @@ int attn_smem_bytes(const b200_llama *m, int n_threads) {
 // One token through the network: the kernel sequence that replaces the 36-nodes-per-layer ggml graph.
 MatDesc mat_desc(const GemvPlan &p) {
   MatDesc d = {};
-  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.lp; d.rpt = p.rpt;
+  d.w = p.d_w; d.M = p.M; d.g_total = p.g_total; d.nb = p.nb; d.cb = p.cb; d.lp = p.half_rows ? 0 : p.lp; d.rpt = p.rpt;
   return d;
 }
 
@@ -493,22 +543,53 @@ cudaError_t run_token(b200_llama *m, int n_threads, long long *launches) {
 }
 
 // Upload the concatenated raw rows of the fused matrices and repack them into the tile-major stream.
-struct RowSlice { const uint8_t *p; size_t bytes; };   // whole rows of a host tensor (ggml rows are contiguous)
+struct RowSlice { const HostTensor *t; int row0, n_rows; };   // rows [row0, row0 + n_rows) of a (merged) tensor
 
-RowSlice rows_of(const HostTensor &t, int row0, int n_rows) {
-  const size_t row_bytes = t.data.size() / (size_t) t.ne[1];
-  return RowSlice{t.data.data() + (size_t) row0 * row_bytes, (size_t) n_rows * row_bytes};
+RowSlice rows_of(const HostTensor &t, int row0, int n_rows) { return RowSlice{&t, row0, n_rows}; }
+
+// rows [row0, row0 + n) of the merged tensor -> contiguous bytes at dst (host)
+void gather_rows(const HostTensor &t, int row0, int n, uint8_t *dst) {
+  const size_t rb = t.row_bytes;
+  if (t.n_parts == 1) { memcpy(dst, t.part[0] + (size_t) row0 * rb, (size_t) n * rb); return; }
+  if (t.split == 1) {                                            // part p holds rows [p*R/n_parts, (p+1)*R/n_parts), PO.mm:478-487
+    const int per = t.ne[1] / t.n_parts;
+    for (int r = row0; r < row0 + n;) {
+      const int pp = r / per, k = std::min(row0 + n, (pp + 1) * per) - r;
+      memcpy(dst + (size_t) (r - row0) * rb, t.part[pp] + (size_t) (r - pp * per) * rb, (size_t) k * rb);
+      r += k;
+    }
+    return;
+  }
+  const size_t w = rb / t.n_parts;                               // part p holds columns [p*K/n_parts, ...) of every row, PO.mm:467-477
+  for (int r = 0; r < n; r++)
+    for (int pp = 0; pp < t.n_parts; pp++)
+      memcpy(dst + (size_t) r * rb + pp * w, t.part[pp] + (size_t) (row0 + r) * w, w);
 }
 
-cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice> &parts, int interleave_half,
+// host rows -> device (contiguous at d_dst), through the pinned double buffer
+cudaError_t upload_rows(Stager &sg, cudaStream_t st, const RowSlice &rs, uint8_t *d_dst) {
+  const size_t rb = rs.t->row_bytes;
+  const int rows_per = (int) std::max<size_t>(1, Stager::kCap / rb);
+  for (int r = 0; r < rs.n_rows; r += rows_per) {
+    const int k = std::min(rows_per, rs.n_rows - r);
+    cudaError_t e = cudaEventSynchronize(sg.ev[sg.cur]);         // the copy that last used this buffer has finished
+    if (e != cudaSuccess) return e;
+    gather_rows(*rs.t, rs.row0 + r, k, sg.buf[sg.cur]);
+    if ((e = cudaMemcpyAsync(d_dst + (size_t) r * rb, sg.buf[sg.cur], (size_t) k * rb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(sg.ev[sg.cur], st)) != cudaSuccess) return e;
+    sg.cur ^= 1;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t upload_matrix(b200_llama *m, Stager &sg, GemvPlan &p, const std::vector<RowSlice> &parts, int interleave_half,
                           uint8_t *d_stage) {
   cudaError_t e = cudaMalloc(&p.d_w, p.bytes);
   if (e != cudaSuccess) return e;
   size_t off = 0;
   for (const RowSlice &t : parts) {
-    e = cudaMemcpyAsync(d_stage + off, t.p, t.bytes, cudaMemcpyHostToDevice, m->stream);
-    if (e != cudaSuccess) return e;
-    off += t.bytes;
+    if ((e = upload_rows(sg, m->stream, t, d_stage + off)) != cudaSuccess) return e;
+    off += (size_t) t.n_rows * t.t->row_bytes;
   }
   const int threads = 256;
   if (p.qtype == 3) {
@@ -531,7 +612,14 @@ cudaError_t upload_matrix(b200_llama *m, GemvPlan &p, const std::vector<RowSlice
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   m->weight_bytes += (long long) p.M * p.nb * (p.qtype == 3 ? 24 : 20);
-  return cudaStreamSynchronize(m->stream);
+  return cudaSuccess;      // stream order protects d_stage: the next matrix's copies queue behind this repack
+}
+
+// small f32 tensors (norm weights): part 0 holds the whole tensor (PO.mm:453-457)
+cudaError_t upload_f32_tensor(const HostTensor &t, float **dst) {
+  cudaError_t e = cudaMalloc(dst, t.row_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, t.part[0], t.row_bytes, cudaMemcpyHostToDevice);
 }
 
 void free_model(b200_llama *m) {
@@ -582,21 +670,29 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   }
   if (device < 0 || device >= n_dev) { set_err(err, errlen, "bad device ordinal %d", device); return fail_code; }
 
-  std::ifstream fin(path, std::ios::binary);
-  if (!fin) { set_err(err, errlen, "failed to open '%s'", path); return fail_code; }                       // PO.mm:100-104
+  // The part files are memory-mapped and parsed in place (PO.mm:98-498 reads them with ifstream into ggml tensors): no host
+  // copy of the weights exists, and what a tensor-parallel rank never uploads it never reads.
+  std::vector<FileMap> maps(1);
+  if (!maps[0].open_file(path)) { set_err(err, errlen, "failed to open '%s'", path); return fail_code; }                // PO.mm:100-104
+  size_t cur = 0;
+  auto take = [&](const FileMap &fm, size_t &at, void *dst, size_t n) -> bool {
+    if (at + n > fm.size) return false;
+    if (dst) memcpy(dst, fm.p + at, n);
+    at += n;
+    return true;
+  };
   uint32_t magic = 0;
-  fin.read((char *) &magic, sizeof(magic));
-  if (magic != 0x67676d6c) { set_err(err, errlen, "invalid model file '%s' (bad magic)", path); return fail_code; }   // PO.mm:110-114
+  if (!take(maps[0], cur, &magic, 4) || magic != 0x67676d6c) { set_err(err, errlen, "invalid model file '%s' (bad magic)", path); return fail_code; }   // PO.mm:110-114
 
   b200_llama *m = new b200_llama();
   struct Guard { b200_llama *p; ~Guard() { if (p) free_model(p); } } guard{m};
   m->device = device;
   m->tp_rank = tp_rank; m->tp_size = tp_size;
   int32_t hp[7] = {0};
-  fin.read((char *) hp, sizeof(hp));                                                                        // PO.mm:124-131
+  const bool hp_ok = take(maps[0], cur, hp, sizeof(hp));                                                    // PO.mm:124-131
   m->n_vocab = hp[0]; m->n_embd = hp[1]; m->n_mult = hp[2]; m->n_head = hp[3]; m->n_layer = hp[4]; m->n_rot = hp[5]; m->f16 = hp[6];
   m->n_ctx = n_ctx;
-  if (!fin || m->n_vocab <= 0 || m->n_embd <= 0 || m->n_mult <= 0 || m->n_head <= 0 || m->n_layer <= 0 || n_ctx <= 0) {
+  if (!hp_ok || m->n_vocab <= 0 || m->n_vocab > (1 << 24) || m->n_embd <= 0 || m->n_mult <= 0 || m->n_head <= 0 || m->n_layer <= 0 || n_ctx <= 0) {
     set_err(err, errlen, "invalid model file '%s' (bad header)", path);
     return fail_code;
   }
@@ -623,10 +719,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   m->id_to_token.resize(m->n_vocab);
   for (int i = 0; i < m->n_vocab; i++) {                                                                    // PO.mm:149-163
     uint32_t len = 0;
-    fin.read((char *) &len, sizeof(len));
-    if (!fin || len > (1u << 20)) { set_err(err, errlen, "invalid model file '%s' (bad vocab)", path); return fail_code; }
-    m->id_to_token[i].resize(len);
-    fin.read(&m->id_to_token[i][0], len);
+    if (!take(maps[0], cur, &len, 4) || len > (1u << 20) || cur + len > maps[0].size) { set_err(err, errlen, "invalid model file '%s' (bad vocab)", path); return fail_code; }
+    m->id_to_token[i].assign((const char *) maps[0].p + cur, len);
+    cur += len;
   }
   switch (m->f16) {                                                                                         // PO.mm:169-180
     case 2: case 3: break;
@@ -637,8 +732,7 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
       set_err(err, errlen, "invalid model file '%s' (bad f16 value %d)", path, m->f16);
       return fail_code;
   }
-  const size_t file_offset = (size_t) fin.tellg();
-  fin.close();
+  const size_t file_offset = cur;
 
   // expected tensors, PO.mm:246-286
   const int E = m->n_embd, F = m->n_ff, V = m->n_vocab;
@@ -646,9 +740,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   const size_t BPB = QT == 3 ? 24 : 20;    // bytes per 32-weight block (ggml.c:2039-2040)
   std::map<std::string, HostTensor> tensors;
   auto expect = [&](const std::string &name, int ne0, int ne1, int n_dims) {
-    HostTensor t; t.n_dims = n_dims; t.ne[0] = ne0; t.ne[1] = ne1;
-    t.data.resize(n_dims == 1 ? (size_t) ne0 * 4 : (size_t) ne1 * (ne0 / 32) * BPB);
-    tensors[name] = std::move(t);
+    HostTensor t; t.n_dims = n_dims; t.ne[0] = ne0; t.ne[1] = ne1; t.n_parts = n_dims == 1 ? 1 : n_parts;
+    t.row_bytes = n_dims == 1 ? (size_t) ne0 * 4 : (size_t) (ne0 / 32) * BPB;
+    tensors[name] = t;
   };
   expect("tok_embeddings.weight", E, V, 2);
   expect("norm.weight", E, 1, 1);
@@ -667,25 +761,29 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   }
   std::map<std::string, int> seen;
 
+  maps.resize(n_parts);
   for (int part = 0; part < n_parts; part++) {                                                              // PO.mm:312-495
     std::string fname = path;
     if (part > 0) fname += "." + std::to_string(part);
-    std::ifstream fp(fname, std::ios::binary);
-    if (!fp) { set_err(err, errlen, "failed to open '%s'", fname.c_str()); return fail_code; }
-    fp.seekg(file_offset);
-    while (true) {
+    if (part > 0 && !maps[part].open_file(fname.c_str())) { set_err(err, errlen, "failed to open '%s'", fname.c_str()); return fail_code; }
+    const FileMap &fm = maps[part];
+    size_t at = file_offset;
+    while (at < fm.size) {
       int32_t n_dims = 0, length = 0, ftype = 0;
-      fp.read((char *) &n_dims, 4); fp.read((char *) &length, 4); fp.read((char *) &ftype, 4);
-      if (fp.eof()) break;
-      if (!fp || n_dims < 1 || n_dims > 2 || length <= 0 || length > 255) {
+      if (!take(fm, at, &n_dims, 4) || !take(fm, at, &length, 4) || !take(fm, at, &ftype, 4) ||
+          n_dims < 1 || n_dims > 2 || length <= 0 || length > 255) {
         set_err(err, errlen, "corrupt tensor record in '%s'", fname.c_str());
         return fail_code;
       }
       int32_t ne[2] = {1, 1};
       int64_t nelements = 1;
-      for (int i = 0; i < n_dims; i++) { fp.read((char *) &ne[i], 4); nelements *= ne[i]; }
-      std::string name(length, 0);
-      fp.read(&name[0], length);
+      for (int i = 0; i < n_dims; i++) {
+        if (!take(fm, at, &ne[i], 4) || ne[i] <= 0) { set_err(err, errlen, "corrupt tensor record in '%s'", fname.c_str()); return fail_code; }
+        nelements *= ne[i];
+      }
+      if (at + (size_t) length > fm.size) { set_err(err, errlen, "corrupt tensor record in '%s'", fname.c_str()); return fail_code; }
+      std::string name((const char *) fm.p + at, (size_t) length);
+      at += (size_t) length;
       auto it = tensors.find(name);
       if (it == tensors.end()) { set_err(err, errlen, "unknown tensor '%s' in model file", name.c_str()); return fail_code; }   // PO.mm:352-356
       HostTensor &t = it->second;
@@ -697,11 +795,12 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
         else split_type = 1;
       } else if (name.find("output") != std::string::npos) split_type = 1;
 
+      size_t nbytes = 0;
       if (n_dims == 1) {
         if (t.n_dims != 1 || (int64_t) t.ne[0] != nelements) { set_err(err, errlen, "tensor '%s' has wrong size in model file", name.c_str()); return fail_code; }
         if (ftype != 0) { set_err(err, errlen, "tensor '%s': 1-D tensors must be f32 (ftype %d)", name.c_str(), ftype); return fail_code; }
-        if (part == 0) fp.read((char *) t.data.data(), t.data.size());                                      // PO.mm:453-457
-        else fp.seekg(t.data.size(), std::ios::cur);
+        nbytes = t.row_bytes;
+        if (part == 0) t.part[0] = fm.p + at;                                                               // PO.mm:453-457
       } else {
         if (t.n_dims != 2 || (int64_t) t.ne[0] * t.ne[1] / n_parts != nelements) { set_err(err, errlen, "tensor '%s' has wrong size in model file", name.c_str()); return fail_code; }
         const bool ok = split_type == 0 ? (t.ne[0] / n_parts == ne[0] && t.ne[1] == ne[1]) : (t.ne[0] == ne[0] && t.ne[1] / n_parts == ne[1]);
@@ -712,22 +811,12 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
         }
         if (ftype != QT) { set_err(err, errlen, "tensor '%s': ftype %d in a type-%d model file", name.c_str(), ftype, QT); return fail_code; }
         if (ne[0] % 64 != 0) { set_err(err, errlen, "tensor '%s': row length %d is not a multiple of 64", name.c_str(), ne[0]); return fail_code; }   // PO.mm:437
-        const size_t row_size = (size_t) t.ne[0] / 32 * BPB;
-        if (n_parts == 1) {
-          fp.read((char *) t.data.data(), t.data.size());
-        } else if (split_type == 0) {                                                                       // PO.mm:467-477
-          for (int i1 = 0; i1 < ne[1]; ++i1) {
-            const size_t offset = (size_t) i1 * row_size + ((size_t) part * ne[0] / 32) * BPB;
-            fp.read((char *) t.data.data() + offset, row_size / n_parts);
-          }
-        } else {                                                                                            // PO.mm:478-487
-          for (int i1 = 0; i1 < ne[1]; ++i1) {
-            const size_t offset_row = ((size_t) i1 + (size_t) part * ne[1]) * row_size;
-            fp.read((char *) t.data.data() + offset_row, row_size);
-          }
-        }
+        t.split = split_type;
+        t.part[part] = fm.p + at;          // merged on the way to the GPU (gather_rows): PO.mm:467-487
+        nbytes = t.row_bytes * (size_t) t.ne[1] / (size_t) n_parts;
       }
-      if (!fp) { set_err(err, errlen, "unexpected end of file in '%s' (tensor '%s')", fname.c_str(), name.c_str()); return fail_code; }
+      if (at + nbytes > fm.size) { set_err(err, errlen, "unexpected end of file in '%s' (tensor '%s')", fname.c_str(), name.c_str()); return fail_code; }
+      at += nbytes;
       seen[name]++;
     }
   }
@@ -750,11 +839,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   CUDA_TRY(cudaMalloc(&d_stage, stage_cap));
   struct StageGuard { uint8_t *p; ~StageGuard() { cudaFree(p); } } sguard{d_stage};
 
-  auto upload_f32 = [&](const HostTensor &t, float **dst) -> cudaError_t {
-    cudaError_t e = cudaMalloc(dst, t.data.size());
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, t.data.data(), t.data.size(), cudaMemcpyHostToDevice);
-  };
+  Stager stager;
+  CUDA_TRY(stager.init());
+  auto upload_f32 = [&](const HostTensor &t, float **dst) -> cudaError_t { return upload_f32_tensor(t, dst); };
   // the tensor-core prefill path keeps a second copy of the Q4_0 weights in its own tile layout (+1x weight bytes of HBM)
   m->want_tc_copy = QT == 2 && tp_size == 1 && env_int("B200_PREFILL_COPY", 1) != 0 && !B200_IMMA;
   const int lp_small = env_int("B200_LP_SMALL", 0), lp_qkv = env_int("B200_LP_QKV", 0), lp_w13 = env_int("B200_LP_W13", 0), lp_out = env_int("B200_LP_OUT", 0);
@@ -767,26 +854,28 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     const std::string p = "layers." + std::to_string(i) + ".";
     b200_llama::Layer &L = m->layers[i];
     L.qkv = make_plan(3 * El, E, m->n_sm, lp_qkv, QT);
-    CUDA_TRY(upload_matrix(m, L.qkv, {rows_of(tensors[p + "attention.wq.weight"], e0, El), rows_of(tensors[p + "attention.wk.weight"], e0, El),
+    CUDA_TRY(upload_matrix(m, stager, L.qkv, {rows_of(tensors[p + "attention.wq.weight"], e0, El), rows_of(tensors[p + "attention.wk.weight"], e0, El),
                                       rows_of(tensors[p + "attention.wv.weight"], e0, El)}, 0, d_stage));
     L.wo = make_plan(El, E, m->n_sm, lp_small, QT);
-    CUDA_TRY(upload_matrix(m, L.wo, {rows_of(tensors[p + "attention.wo.weight"], e0, El)}, 0, d_stage));
+    CUDA_TRY(upload_matrix(m, stager, L.wo, {rows_of(tensors[p + "attention.wo.weight"], e0, El)}, 0, d_stage));
     L.w13 = make_plan(2 * Fl, E, m->n_sm, lp_w13, QT);
-    CUDA_TRY(upload_matrix(m, L.w13, {rows_of(tensors[p + "feed_forward.w1.weight"], f0, Fl), rows_of(tensors[p + "feed_forward.w3.weight"], f0, Fl)}, Fl, d_stage));
+    CUDA_TRY(upload_matrix(m, stager, L.w13, {rows_of(tensors[p + "feed_forward.w1.weight"], f0, Fl), rows_of(tensors[p + "feed_forward.w3.weight"], f0, Fl)}, Fl, d_stage));
     L.w2 = make_plan(El, F, m->n_sm, lp_small, QT);
-    CUDA_TRY(upload_matrix(m, L.w2, {rows_of(tensors[p + "feed_forward.w2.weight"], e0, El)}, 0, d_stage));
+    CUDA_TRY(upload_matrix(m, stager, L.w2, {rows_of(tensors[p + "feed_forward.w2.weight"], e0, El)}, 0, d_stage));
     CUDA_TRY(upload_f32(tensors[p + "attention_norm.weight"], &L.attn_norm));
     CUDA_TRY(upload_f32(tensors[p + "ffn_norm.weight"], &L.ffn_norm));
   }
   m->out = make_plan(Vl, E, m->n_sm, lp_out, QT);
-  CUDA_TRY(upload_matrix(m, m->out, {rows_of(tensors["output.weight"], v0, Vl)}, 0, d_stage));
+  CUDA_TRY(upload_matrix(m, stager, m->out, {rows_of(tensors["output.weight"], v0, Vl)}, 0, d_stage));
   CUDA_TRY(upload_f32(tensors["norm.weight"], &m->d_norm));
   {
     const HostTensor &t = tensors["tok_embeddings.weight"];
-    CUDA_TRY(cudaMalloc(&m->d_tok_emb, t.data.size()));
-    CUDA_TRY(cudaMemcpy(m->d_tok_emb, t.data.data(), t.data.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&m->d_tok_emb, t.row_bytes * (size_t) t.ne[1]));
+    CUDA_TRY(upload_rows(stager, m->stream, rows_of(t, 0, t.ne[1]), m->d_tok_emb));
   }
+  CUDA_TRY(cudaStreamSynchronize(m->stream));       // every staged copy and repack has finished: the mappings can go
   tensors.clear();
+  maps.clear();
 
   const size_t kv_bytes = (size_t) m->n_layer * n_ctx * E * sizeof(float);                                  // PO.mm:297-301
   CUDA_TRY(cudaMalloc(&m->d_k, kv_bytes));
@@ -1124,9 +1213,7 @@ cudaError_t enqueue_batch_chunk(b200_llama *m, int n_threads, int n_past_call, i
   if (last_chunk) {
     // the caller gets the logits of the LAST token only (PO.mm:724-725): final norm + lm_head on one column
     batch_prep_kernel<1><<<1, 256, 0, st>>>(m->b_x + (size_t) (n - 1) * E, m->d_norm, m->b_act, E);   // PO.mm:694-701
-    uint8_t *act_save = m->b_act;
     if ((e = launch_gemm_cols(m, m->out, 1, m->d_logits, m->n_vocab, &nl)) != cudaSuccess) return e;  // PO.mm:705
-    (void) act_save;
     nl += 1;
   }
   if (launches) *launches += nl;
@@ -1529,8 +1616,9 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
   tmp.device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
   GemvPlan p = make_plan(M, K, env_int("B200_NUM_CTAS", prop.multiProcessorCount), lane_pairs, qtype);
-  HostTensor t;
-  t.data.assign((const uint8_t *) w_ggml, (const uint8_t *) w_ggml + (size_t) M * (K / 32) * (qtype == 3 ? 24 : 20));
+  HostTensor t;             // the caller's ggml rows, referenced in place
+  t.n_dims = 2; t.ne[0] = K; t.ne[1] = M; t.part[0] = (const uint8_t *) w_ggml; t.row_bytes = (size_t) (K / 32) * (qtype == 3 ? 24 : 20);
+  Stager stager;
   uint8_t *d_stage = nullptr;
   float *d_x = nullptr, *d_out = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1543,8 +1631,10 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
   };
 #define MV_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e__), #expr); cleanup(); return fail_code; } } while (0)
   MV_TRY(configure_kernels());
-  MV_TRY(cudaMalloc(&d_stage, t.data.size()));
-  MV_TRY(upload_matrix(&tmp, p, {RowSlice{t.data.data(), t.data.size()}}, 0, d_stage));
+  MV_TRY(stager.init());
+  MV_TRY(cudaMalloc(&d_stage, t.row_bytes * (size_t) M));
+  MV_TRY(upload_matrix(&tmp, stager, p, {rows_of(t, 0, M)}, 0, d_stage));
+  MV_TRY(cudaStreamSynchronize(tmp.stream));
   MV_TRY(cudaMalloc(&d_x, (size_t) K * 4));
   MV_TRY(cudaMalloc(&d_out, (size_t) M * 4));
   MV_TRY(cudaMemcpy(d_x, x, (size_t) K * 4, cudaMemcpyHostToDevice));
@@ -1568,6 +1658,78 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
 #undef MV_TRY
   cleanup();
   return rc;
+}
+
+
+/* out[N][M] = W[M x K] (Q4_0, ggml rows) x the N columns x[N][K], every column computed exactly as
+ * ggml_compute_forward_mul_mat_q4_0_f32 does (ggml.c:6199-6222).  path 0: CUDA-core multi-column loop (weights streamed
+ * once per 8 columns), path 1: tcgen05 / TMEM kernel.  kernel_ms: best-of-5 device time of the mat-mul kernel(s) alone. */
+int b200_q4_0_matmul(int device, const void *w_ggml, int M, int K, const float *x, int N, float *out, int path,
+                     float *kernel_ms, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { set_err(err, errlen, "no CUDA device available (this library has no CPU path)"); return fail_code; }
+  if (M < 1 || K < 64 || K % 64 != 0 || N < 1 || N > 4096) { set_err(err, errlen, "bad shape %d x %d, N %d", M, K, N); return fail_code; }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  b200_llama tmp;
+  tmp.device = device;
+  tmp.n_sm = env_int("B200_NUM_CTAS", prop.multiProcessorCount);
+  tmp.want_tc_copy = path == 1;
+  CUDA_TRY(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+  GemvPlan p = make_plan(M, K, tmp.n_sm, 0, 2);
+  const size_t wbytes = (size_t) M * (K / 32) * 20;
+  uint8_t *d_stage = nullptr;
+  float *d_x = nullptr, *d_out = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const int npad = (N + TC_T - 1) / TC_T * TC_T, nbq = (K / 32 + 3) / 4;
+  auto cleanup = [&]() {
+    cudaFree(d_stage); cudaFree(d_x); cudaFree(d_out); cudaFree(p.d_w); cudaFree(p.d_wtc); cudaFree(tmp.b_act); cudaFree(tmp.b_xh); cudaFree(tmp.b_dxT);
+    tmp.b_act = nullptr; tmp.b_xh = nullptr; tmp.b_dxT = nullptr;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaStreamDestroy(tmp.stream);
+    tmp.stream = nullptr;
+  };
+#define MM_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e__), #expr); cleanup(); return fail_code; } } while (0)
+  MM_TRY(configure_kernels());
+  MM_TRY(cudaMalloc(&d_stage, wbytes));
+  {
+    HostTensor t;           // the caller's ggml rows, referenced in place
+    t.n_dims = 2; t.ne[0] = K; t.ne[1] = M; t.part[0] = (const uint8_t *) w_ggml; t.row_bytes = (size_t) (K / 32) * 20;
+    Stager stager;
+    MM_TRY(stager.init());
+    MM_TRY(upload_matrix(&tmp, stager, p, {rows_of(t, 0, M)}, 0, d_stage));
+    MM_TRY(cudaStreamSynchronize(tmp.stream));
+  }
+  MM_TRY(cudaMalloc(&d_x, (size_t) N * K * 4));
+  MM_TRY(cudaMalloc(&d_out, (size_t) N * M * 4));
+  MM_TRY(cudaMalloc(&tmp.b_act, (size_t) N * batch_act_bytes(K / 32)));
+  if (path == 1) {
+    MM_TRY(cudaMalloc(&tmp.b_xh, (size_t) npad / TC_T * nbq * TC_XH_BYTES));
+    MM_TRY(cudaMalloc(&tmp.b_dxT, (size_t) npad / TC_T * nbq * TC_DX_BYTES));
+  }
+  MM_TRY(cudaMemcpy(d_x, x, (size_t) N * K * 4, cudaMemcpyHostToDevice));
+  MM_TRY(cudaEventCreate(&e0));
+  MM_TRY(cudaEventCreate(&e1));
+  batch_prep_kernel<0><<<N, 256, 0, tmp.stream>>>(d_x, nullptr, tmp.b_act, K);
+  MM_TRY(cudaGetLastError());
+  float best = 1e30f;
+  for (int i = 0; i < (kernel_ms ? 5 : 1); i++) {
+    MM_TRY(cudaEventRecord(e0, tmp.stream));
+    MM_TRY(path == 1 ? launch_gemm_tc(&tmp, p, N, d_out, M, nullptr) : launch_gemm_cols(&tmp, p, N, d_out, M, nullptr));
+    MM_TRY(cudaEventRecord(e1, tmp.stream));
+    MM_TRY(cudaStreamSynchronize(tmp.stream));
+    float ms = 0;
+    MM_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  if (kernel_ms) *kernel_ms = best;
+  MM_TRY(cudaMemcpy(out, d_out, (size_t) N * M * 4, cudaMemcpyDeviceToHost));
+#undef MM_TRY
+  cleanup();
+  return B200_LLAMA_OK;
 }
 
 int b200_q4_0_matvec(int device, const void *w_ggml, int M, int K, const float *x, float *out, int lane_pairs,

@@ -50,6 +50,9 @@
 #ifndef B200_HINTS
 #define B200_HINTS 1        // arrival-hint counters in front of the flagged-word reads (polite polling)
 #endif
+#ifndef B200_JITTER
+#define B200_JITTER 0       // stress build: every CTA sleeps a pseudo-random 0-4 us before every phase (soak test of the barrier-free exchange)
+#endif
 #ifndef B200_NO_MATH
 #define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
 #endif
@@ -649,8 +652,73 @@ __device__ __forceinline__ void gemv_rows(const MatDesc &md, const RowPart rp, c
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
 }
 
+
+// ---- few-row matrices (wo, w2: 28 rows per CTA at 7B; every matrix of a tensor-parallel shard): EIGHT threads per row --------
+// With 4 threads per row such a phase keeps only 4 of the 16 warps busy, one per scheduler, and each of them walks its row
+// at the latency-bound single-warp rate (profiles/r1_f_phase_profile.md: wo 4.1 TB/s, w2 5.2 TB/s from a pre-filled ring).
+// Here thread t8 of a row owns ONE accumulator lane (lane l = t8 = word l/2, low nibbles for even l, high for odd): the same
+// LP = 1 stream, the same per-lane operations (dp4a of the lane's 4 elements, exact int -> float, fma with d_w * d_x), twice
+// the warps, ~0.7x the instructions per thread.  The lanes are not paired, so the fma is a scalar FFMA.
+__device__ __forceinline__ void gemv_rows_half(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
+                                               int S, int stage_bytes, int tid) {
+  const int R = rp.R, cb = md.cb;
+  const int nbq = (md.nb + 3) >> 2, cq = cb >> 2;
+  const int nchunks = (nbq + cq - 1) / cq;
+  const bool active = tid < R * 8;
+  const int g = active ? tid >> 3 : R - 1;
+  const int t8 = tid & 7, t = t8 >> 1, hi = t8 & 1;
+  const uint32_t sh = hi ? 0u : 4u;                      // high nibbles are in place; low nibbles move up by 4
+  const bool warp_active = (tid & ~31) < R * 8;
+  float acc = 0.0f;
+  const int qstride = R * 80;
+
+  for (int k = 0; k < nchunks; k++, ring.next(S)) {
+    const int s = ring.s;
+    mbar_wait(&sm.full[s], ring.par);
+    if (warp_active && !B200_NO_MATH) {
+      const int cqk = min(cq, nbq - k * cq);
+      const uint8_t *st = sm.stages + (size_t) s * stage_bytes;
+      const uint8_t *pw = st + (g * 4 + t) * 16, *ps = st + R * 64 + g * 16;
+      const uint8_t *px = reinterpret_cast<const uint8_t *>(sm.xq + (size_t) t * sm.nbx + k * cb) + hi * 4;
+      const float *pd = sm.dxs + k * cb;
+      uint4 w4 = *reinterpret_cast<const uint4 *>(pw);
+      float4 sc4 = *reinterpret_cast<const float4 *>(ps);
+      for (int q = 0; q < cqk; q++) {
+        // loads of quad q+1 under the math of quad q (one quad past the end of the chunk is still inside this CTA's smem)
+        const uint4 w4n = *reinterpret_cast<const uint4 *>(pw + (q + 1) * qstride);
+        const float4 sc4n = *reinterpret_cast<const float4 *>(ps + (q + 1) * qstride);
+        const float4 dx4 = *reinterpret_cast<const float4 *>(pd + q * 4);
+        const uint2 *xp = reinterpret_cast<const uint2 *>(px + q * 32);          // {lane 2t, lane 2t+1} bytes of 4 blocks; px is offset by hi
+        const int x0 = (int) reinterpret_cast<const uint32_t *>(xp)[0], x1 = (int) reinterpret_cast<const uint32_t *>(xp)[2];
+        const int x2 = (int) reinterpret_cast<const uint32_t *>(xp)[4], x3 = (int) reinterpret_cast<const uint32_t *>(xp)[6];
+        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        const int xx[4] = {x0, x1, x2, x3};
+        const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, dx[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int a8 = (int) and_xor(ww[b] << sh, 0xF0F0F0F0u, 0x80808080u);   // signed bytes 16*(q-8) of this lane
+          const int ib = dp4a_ss(a8, xx[b], 0x4B400000);                          // float bits of 12582912 + 16*isum
+          const float f = fmaf(__int_as_float(ib), 0.0625f, -786432.0f);          // exact (float) isum
+          const float sdx = __fmul_rn(sc[b], dx[b]);                              // _mm256_mul_ps(d0, d1), ggml.c:1431
+          acc = fmaf(sdx, f, acc);                                                // _mm256_fmadd_ps, ggml.c:1457
+        }
+        w4 = w4n; sc4 = sc4n;
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+  }
+  // horizontal sum as ggml.c:1461-1466 with the 8 lanes in 8 consecutive threads: (acc[k] + acc[k+4]), (r0 + r2), (r1 + r3), sum
+  float r = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  if (active && t8 == 0) sm.rowres[g] = r;
+  named_bar_sync(1, MEGA_COMPUTE_THREADS);
+}
+
 __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart rp, const MegaSmem &sm, RingPos &ring,
                                               int S, int stage_bytes, int tid) {
+  if (md.lp == 0) { gemv_rows_half(md, rp, sm, ring, S, stage_bytes, tid); return; }     // LP = 1 stream, 8 threads per row
   const int rpt = (rp.R % md.rpt == 0) ? md.rpt : 1;   // R is a multiple of 4, so 2 and 4 always divide it
   switch (md.lp * 8 + rpt) {
     case 1 * 8 + 1: gemv_rows<1, 1>(md, rp, sm, ring, S, stage_bytes, tid); break;
@@ -967,6 +1035,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
     const int il = step / 5;
     const int kind = il < a.n_layer ? step - 5 * il : PH_OUT;
     const LayerDesc &L = a.layers[il < a.n_layer ? il : 0];
+#if B200_JITTER
+    {   // de-synchronise the CTAs (and the GPUs of a group): the exchange protocol must not depend on arrival order
+      if (tid == 0) {
+        uint32_t hsh = (blockIdx.x * 2654435761u) ^ ((uint32_t) step * 40503u) ^ (epoch * 2246822519u) ^ ((uint32_t) rank * 3266489917u);
+        hsh ^= hsh >> 15; hsh *= 2654435761u; hsh ^= hsh >> 13;
+        __nanosleep(hsh & 4095u);
+      }
+      named_bar_sync(1, MEGA_COMPUTE_THREADS);
+    }
+#endif
     const uint32_t seq = seq0 + (uint32_t) il;
     const uint32_t par = (uint32_t) il & 1u;
 

@@ -65,3 +65,21 @@ def test_batch_equals_token_by_token(small_model):
     finally:
         a.free()
         b.free()
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["cuda-core-columns", "tcgen05"])
+@pytest.mark.parametrize("shape", [(4096, 4096), (1000, 4096), (4096, 11008), (260, 128)])
+def test_matmul_columns_bit_exact(oracle_lib, shape, path):
+    """Kernel-level: out[N][M] = W x N columns must equal ggml_compute_forward_mul_mat_q4_0_f32 bit for bit for every
+    column (BASELINE.json configs[4]: bs in {1, 4, 16}, plus a ragged 33), incl. M that is not a multiple of the 128-row tile."""
+    from llama_swift_b200 import ggml_format as gf
+    M, K = shape
+    rng = np.random.default_rng(M + K)
+    wq = gf.quantize_q4_0((rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32))
+    for N in (1, 4, 16, 33):
+        x = (rng.standard_normal((N, K)) * 1.3).astype(np.float32)
+        x[0, :32] = 0.0
+        want = np.zeros((N, M), np.float32)
+        oracle_lib.ora_mul_mat_q4(2, wq.ctypes.data, M, K, x.ctypes.data, N, want.ctypes.data)
+        got = lsb.q4_0_matmul(wq, x, path=path)
+        assert np.array_equal(bits(got), bits(want)), f"N={N}: max abs diff {np.abs(got - want).max()}"

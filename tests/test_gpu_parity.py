@@ -254,7 +254,7 @@ def test_13b_shapes_vs_oracle(oracle_lib):
         ora.free()
 
 
-def test_resident_model_cache(small_model):
+def test_resident_model_cache(oracle_lib, small_model):
     """the reference re-reads the model file on every run() (PO.mm:790); an acquired model that
     was released is handed back without loading, and a second run over its dirty KV cache gives the same logits."""
     import time
@@ -278,6 +278,11 @@ def test_resident_model_cache(small_model):
         assert b._h.value in (h1, h2)                              # a resident model (one idle copy is kept), not a fresh load
         again = lsb.llama_eval(b, 8, 0, toks)
         assert np.array_equal(bits(again), bits(first))
+        ora = CpuModel(oracle_lib, "ora", small_model, 64)            # ... and both are the oracle's logits
+        try:
+            assert np.array_equal(bits(again), bits(ora.eval(8, 0, toks)))
+        finally:
+            ora.free()
         assert np.array_equal(bits(lsb.llama_eval(b, 8, 5, np.array([int(first.argmax())], np.int32))), bits(step))
         print(f"[cache] first acquire {t_load * 1e3:.0f} ms, re-acquire {t_again * 1e3:.2f} ms")
         assert t_again < 0.05 * t_load + 0.005

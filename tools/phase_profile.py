@@ -15,11 +15,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=8)
 ap.add_argument("--pos", type=int, default=64)
 ap.add_argument("--out", default="")
+ap.add_argument("--tp", type=int, default=1, help="profile a single-process tensor-parallel group of this many GPUs (rank 0's timeline)")
 args = ap.parse_args()
 path = f"/tmp/probe-7b-l{args.layers}.bin"
 if not os.path.exists(path):
     gf.write_synthetic_model(path, gf.HParams(n_layer=args.layers), seed=0, mode="direct")
-m = lsb.llama_model_load(path, n_ctx=max(128, args.pos + 8))
+m = (lsb.llama_model_load(path, n_ctx=max(128, args.pos + 8)) if args.tp == 1 else
+     lsb.llama_model_load_group(path, n_ctx=max(128, args.pos + 8), devices=tuple(range(args.tp))))
 lsb.llama_eval(m, 8, 0, np.arange(3, 11, dtype=np.int32))
 toks, _, ms = m.decode_device(8, 5, args.pos - 8, n_threads=8)     # fill the cache up to pos
 print(f"decode {args.pos - 8} steps: {ms / (args.pos - 8) * 1e3:.1f} us/token")

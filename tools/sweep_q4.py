@@ -1,8 +1,9 @@
-"""BASELINE.json configs[4]: Q4_1 vs Q4_0 mat-vec kernels over the four LLaMA-7B weight shapes, N in {1, 4, 16} columns.
+"""BASELINE.json configs[4]: Q4_1 vs Q4_0 mat-mul kernels over the four LLaMA-7B weight shapes, bs in {1, 4, 16} columns.
 
-The reference evaluates the N columns of a mat-mul independently (ggml.c:6199-6222), and so does this library (N
-single-column passes), so N > 1 is N back-to-back kernel invocations on the same matrix; what the sweep shows is the
-kernel-level cost per column and the achieved weight bandwidth.  Prints a markdown table (development aid / profiles)."""
+Q4_0: bs = 1 is the single-column mat-vec kernel; bs = 4 / 16 are ONE launch of the batch path's mat-mul -- the CUDA-core
+multi-column loop (weights streamed once per 8 columns) and the tcgen05 / TMEM kernel (one 16-token tile).  Q4_1 follows
+the reference's scalar-only kernel (one sequential float chain per row, ggml.c:1584-1626) and has no multi-column form:
+bs > 1 is bs back-to-back launches.  Prints a markdown table (development aid / profiles)."""
 import os
 import sys
 
@@ -13,13 +14,21 @@ import llama_swift_b200 as lsb
 from llama_swift_b200 import ggml_format as gf
 
 rng = np.random.default_rng(0)
-print("| shape (M x K) | type | bytes | us / column | GB/s | N=4 us | N=16 us |")
+print("| shape (M x K) | type | bytes | bs=1 us | GB/s | bs=4 us (cols / tcgen05) | bs=16 us (cols / tcgen05) |")
 print("|---|---|---|---|---|---|---|")
 for (M, K) in [(4096, 4096), (11008, 4096), (4096, 11008), (32000, 4096)]:
     w = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
-    x = rng.standard_normal(K).astype(np.float32)
-    for name, q, fn, bpb in (("Q4_0", gf.quantize_q4_0, lsb.q4_0_matvec, 20), ("Q4_1", gf.quantize_q4_1, lsb.q4_1_matvec, 24)):
-        blk = q(w)
-        out, ms = fn(blk, x, timed=True)           # best of 5 launches, CUDA events
-        nbytes = M * K // 32 * bpb
-        print(f"| {M} x {K} | {name} | {nbytes / 1e6:.1f} MB | {ms * 1e3:.1f} | {nbytes / ms / 1e6:.0f} | {4 * ms * 1e3:.1f} | {16 * ms * 1e3:.1f} |", flush=True)
+    x = rng.standard_normal((16, K)).astype(np.float32)
+    blk = gf.quantize_q4_0(w)
+    _, ms1 = lsb.q4_0_matvec(blk, x[0], timed=True)
+    cells = []
+    for n in (4, 16):
+        _, a = lsb.q4_0_matmul(blk, x[:n], path=0, timed=True)
+        _, b = lsb.q4_0_matmul(blk, x[:n], path=1, timed=True)
+        cells.append(f"{a * 1e3:.1f} / {b * 1e3:.1f}")
+    nbytes = M * K // 32 * 20
+    print(f"| {M} x {K} | Q4_0 | {nbytes / 1e6:.1f} MB | {ms1 * 1e3:.1f} | {nbytes / ms1 / 1e6:.0f} | {cells[0]} | {cells[1]} |", flush=True)
+    blk1 = gf.quantize_q4_1(w)
+    _, ms = lsb.q4_1_matvec(blk1, x[0], timed=True)
+    nbytes = M * K // 32 * 24
+    print(f"| {M} x {K} | Q4_1 | {nbytes / 1e6:.1f} MB | {ms * 1e3:.1f} | {nbytes / ms / 1e6:.0f} | {4 * ms * 1e3:.1f} (4 launches) | {16 * ms * 1e3:.1f} (16 launches) |", flush=True)
