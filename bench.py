@@ -357,6 +357,7 @@ def main():
     ap.add_argument("--threads", type=int, default=8, help="reference thread count mirrored by the V*P partition (Swift default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the 24-step comparison with the reference CPU path")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the informational run of N independent generations")
     ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
                     help="N > 1: tp = ONE bs=1 generation over all GPUs (rows of every matrix split over the ranks; the metric "
                          "BASELINE.json names); replicas = N independent generations")
@@ -541,6 +542,22 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_s = dist_util.max_over_ranks(e2e_s, "cuda")
 
+    # ---- for information at N > 1: what the same GPUs deliver as N independent bs = 1 generations (weak scaling) ----
+    replicas = None
+    if tp and not args.no_replicas:
+        os.environ["B200_PREFILL_COPY"] = "0"          # decode only: no second weight layout
+        rep = lsb.llama_model_load(path, n_ctx=n_ctx, device=local_rank)
+        rfirst = int(lsb.llama_eval(rep, args.threads, 0, np.array(PROMPT, np.int32)).argmax())
+        rep.decode_device(N_PROMPT, rfirst, warmup, n_threads=args.threads)
+        rfirst = int(lsb.llama_eval(rep, args.threads, 0, np.array(PROMPT, np.int32)).argmax())
+        sync_all()
+        _, _, rms = rep.decode_device(N_PROMPT, rfirst, steps, n_threads=args.threads)
+        sync_all()
+        rms = dist_util.max_over_ranks(rms, "cuda")
+        rep.free()
+        replicas = {"value": world * steps / (rms * 1e-3), "unit": "tokens/s", "scaling": "weak",
+                    "note": "%d independent bs=1 generations, one whole model per GPU, same step count; device-resident loop, max over ranks" % world}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -598,7 +615,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": jobs * steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": n_vocab * 4,
                     "note": "b200_llama_eval per token: token id by value, logits to pinned host memory, host arg-max"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "replicas": replicas}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -268,6 +269,9 @@ struct HostTensor {
 struct FileMap {
   const uint8_t *p = nullptr;
   size_t size = 0;
+  FileMap() = default;
+  FileMap(const FileMap &) = delete;
+  FileMap &operator=(const FileMap &) = delete;
   ~FileMap() { if (p) munmap(const_cast<uint8_t *>(p), size); }
   bool open_file(const char *path) {
     const int fd = ::open(path, O_RDONLY);
@@ -672,8 +676,9 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
 
   // The part files are memory-mapped and parsed in place (PO.mm:98-498 reads them with ifstream into ggml tensors): no host
   // copy of the weights exists, and what a tensor-parallel rank never uploads it never reads.
-  std::vector<FileMap> maps(1);
-  if (!maps[0].open_file(path)) { set_err(err, errlen, "failed to open '%s'", path); return fail_code; }                // PO.mm:100-104
+  std::vector<std::unique_ptr<FileMap>> maps;       // (a FileMap owns its mapping: never copied)
+  maps.emplace_back(new FileMap());
+  if (!maps[0]->open_file(path)) { set_err(err, errlen, "failed to open '%s'", path); return fail_code; }                // PO.mm:100-104
   size_t cur = 0;
   auto take = [&](const FileMap &fm, size_t &at, void *dst, size_t n) -> bool {
     if (at + n > fm.size) return false;
@@ -682,14 +687,14 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
     return true;
   };
   uint32_t magic = 0;
-  if (!take(maps[0], cur, &magic, 4) || magic != 0x67676d6c) { set_err(err, errlen, "invalid model file '%s' (bad magic)", path); return fail_code; }   // PO.mm:110-114
+  if (!take(*maps[0], cur, &magic, 4) || magic != 0x67676d6c) { set_err(err, errlen, "invalid model file '%s' (bad magic)", path); return fail_code; }   // PO.mm:110-114
 
   b200_llama *m = new b200_llama();
   struct Guard { b200_llama *p; ~Guard() { if (p) free_model(p); } } guard{m};
   m->device = device;
   m->tp_rank = tp_rank; m->tp_size = tp_size;
   int32_t hp[7] = {0};
-  const bool hp_ok = take(maps[0], cur, hp, sizeof(hp));                                                    // PO.mm:124-131
+  const bool hp_ok = take(*maps[0], cur, hp, sizeof(hp));                                                    // PO.mm:124-131
   m->n_vocab = hp[0]; m->n_embd = hp[1]; m->n_mult = hp[2]; m->n_head = hp[3]; m->n_layer = hp[4]; m->n_rot = hp[5]; m->f16 = hp[6];
   m->n_ctx = n_ctx;
   if (!hp_ok || m->n_vocab <= 0 || m->n_vocab > (1 << 24) || m->n_embd <= 0 || m->n_mult <= 0 || m->n_head <= 0 || m->n_layer <= 0 || n_ctx <= 0) {
@@ -719,8 +724,8 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   m->id_to_token.resize(m->n_vocab);
   for (int i = 0; i < m->n_vocab; i++) {                                                                    // PO.mm:149-163
     uint32_t len = 0;
-    if (!take(maps[0], cur, &len, 4) || len > (1u << 20) || cur + len > maps[0].size) { set_err(err, errlen, "invalid model file '%s' (bad vocab)", path); return fail_code; }
-    m->id_to_token[i].assign((const char *) maps[0].p + cur, len);
+    if (!take(*maps[0], cur, &len, 4) || len > (1u << 20) || cur + len > maps[0]->size) { set_err(err, errlen, "invalid model file '%s' (bad vocab)", path); return fail_code; }
+    m->id_to_token[i].assign((const char *) maps[0]->p + cur, len);
     cur += len;
   }
   switch (m->f16) {                                                                                         // PO.mm:169-180
@@ -761,12 +766,14 @@ int load_impl(const char *path, int n_ctx, int device, int tp_rank, int tp_size,
   }
   std::map<std::string, int> seen;
 
-  maps.resize(n_parts);
   for (int part = 0; part < n_parts; part++) {                                                              // PO.mm:312-495
     std::string fname = path;
     if (part > 0) fname += "." + std::to_string(part);
-    if (part > 0 && !maps[part].open_file(fname.c_str())) { set_err(err, errlen, "failed to open '%s'", fname.c_str()); return fail_code; }
-    const FileMap &fm = maps[part];
+    if (part > 0) {
+      maps.emplace_back(new FileMap());
+      if (!maps[part]->open_file(fname.c_str())) { set_err(err, errlen, "failed to open '%s'", fname.c_str()); return fail_code; }
+    }
+    const FileMap &fm = *maps[part];
     size_t at = file_offset;
     while (at < fm.size) {
       int32_t n_dims = 0, length = 0, ftype = 0;
