@@ -440,6 +440,7 @@ cudaError_t enqueue_token_mega(b200_llama *m, int n_threads, long long *launches
   a.xs_floats = m->mega_xs_floats;
   a.ll_stage = m->mega_ll_stage;
   a.prof = m->d_prof; a.prof_marks = m->prof_marks;
+  a.pace_ps_per_byte = env_int("B200_PACE_PS_PER_BYTE", 0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(m->n_sm);
   cfg.blockDim = dim3(MEGA_THREADS);

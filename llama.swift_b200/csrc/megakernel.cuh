@@ -53,6 +53,9 @@
 #ifndef B200_JITTER
 #define B200_JITTER 0       // stress build: every CTA sleeps a pseudo-random 0-4 us before every phase (soak test of the barrier-free exchange)
 #endif
+#ifndef B200_PROF_ATT
+#define B200_PROF_ATT 0     // development: 5 timeline stamps inside every attention phase (stored in the spare tail of the profile array)
+#endif
 #ifndef B200_NO_MATH
 #define B200_NO_MATH 0      // development: 1 = consume the ring without doing the math (delivery-rate ceiling; wrong results)
 #endif
@@ -118,6 +121,7 @@ struct TokenArgs {
   int S, stage_bytes;
   int xs_floats;            // size of the f32 scratch area (attention scores): >= n_ctx
   int ll_stage;             // != 0: shared memory has room to stage one n_embd-sized flagged vector (TMA bulk copy)
+  int pace_ps_per_byte;     // != 0: the loader spaces its bulk copies so that this SM streams at most 1 byte per that many ps (experiment)
   long long *prof;          // optional [gridDim.x][prof_marks] globaltimer stamps (development profiler), else null
   int prof_marks;
 };
@@ -732,6 +736,11 @@ __device__ __forceinline__ void gemv_dispatch(const MatDesc &md, const RowPart r
 #endif
 
 // ---- attention phase for (head h, output quarter qr): K.Q for all positions, soft_max, V.P for 32 dims --------------
+#if B200_PROF_ATT
+#define ATT_MARK(k) do { if (a.prof && tid == 0) a.prof[(size_t) blockIdx.x * a.prof_marks + 18 * a.n_layer + 8 + 5 * (int) (seq - 1u - ld_vol_u32(a.epoch) * (uint32_t) (a.n_layer + 2)) + (k)] = globaltimer_ns(); } while (0)
+#else
+#define ATT_MARK(k) do { } while (0)
+#endif
 __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerDesc &L, const MegaSmem &sm, int h, int qr,
                                                 int pos, int p_part, uint32_t att_off, const uint2 *qkv_ll, uint32_t seq,
                                                 long long limit, int tid) {
@@ -740,6 +749,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   const int E = a.n_embd;
   const int p_valid = pos + 1;      // diag_mask_inf: columns > n_past + i are -inf -> probability 0 (ggml.c:6946-6953)
   float *sc = sm.xs;
+  ATT_MARK(0);
   // This token's roped Q, its K row and V row arrive as flagged words straight from the CTAs that computed them (no
   // grid barrier between the mat-vec and the attention); rows of earlier positions come from the f32 cache, whose
   // current row is written for FUTURE tokens only.
@@ -766,6 +776,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     }
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
+  ATT_MARK(1);      // q / k / v of this token have arrived
   float qv[4], kcur[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) { qv[i] = sm.qkc[lane + 32 * i]; kcur[i] = sm.qkc[128 + lane + 32 * i]; }
@@ -811,6 +822,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     for (int i = 0; i < VB; i++) vpre[i] = (j0 + i < j1) ? (j0 + i == pos ? vcur : __ldcg(vp + (size_t) (j0 + i) * E)) : 0.0f;
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
+  ATT_MARK(2);      // K.Q done
   // soft_max, ggml.c:7019-7041
   float mx = -CUDART_INF_F;
   for (int j = tid; j < p_valid; j += MEGA_COMPUTE_THREADS) mx = fmaxf(mx, sc[j]);
@@ -826,6 +838,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
   const float inv = (float) (1.0 / sum);
   for (int j = tid; j < p_valid; j += MEGA_COMPUTE_THREADS) sc[j] = __fmul_rn(sc[j], inv);   // ggml_vec_scale_f32, ggml.c:7041
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
+  ATT_MARK(3);      // soft_max done
   // V.P: reference thread t owns columns [t*dc, (t+1)*dc) (ggml.c:5628-5632), FINALIZE adds buffers in order (5570-5574)
   for (int t = warp; t < nth; t += NW) {
     const int j0 = t * dc;
@@ -872,6 +885,7 @@ __device__ __forceinline__ void attention_phase(const TokenArgs &a, const LayerD
     sm.part[t * 32 + lane] = acc;
   }
   named_bar_sync(1, MEGA_COMPUTE_THREADS);
+  ATT_MARK(4);      // V.P chains done
   if (warp == 0) {
     float o = sm.part[lane];
     for (int t = 1; t < nth; t++) o = __fadd_rn(o, sm.part[t * 32 + lane]);
@@ -946,6 +960,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
       const uint64_t l2pol = l2_policy_evict_first();
 #endif
       const int n_mats = 4 * a.n_layer + 1;
+      long long pace_next = 0;
 #if B200_IDLE_PREFETCH
       // second cursor over the same schedule: (matrix pf_mi, chunk pf_k) is chunk number pf_g of this CTA's stream
       int pf_mi = 0, pf_k = 0;
@@ -984,6 +999,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_token_kernel(const __g
           if (!mbar_wait(&sm.empty[s], g.par ^ 1u, a.spin_limit)) return;   // (the consumers may be waiting for another GPU); abandoned: stop streaming
           const int cqk = min(cq, nbq - k * cq);
           const uint32_t bytes = (uint32_t) cqk * rp.R * 80;
+          if (a.pace_ps_per_byte) {
+            // paced streaming: a steady rate instead of bursts at full HBM speed, so that the latency-critical exchange
+            // traffic of the serial phases meets shorter queues in L2
+            while (globaltimer_ns() < pace_next) __nanosleep(100);
+            pace_next = max(pace_next, globaltimer_ns() - 2000) + ((long long) bytes * a.pace_ps_per_byte) / 1000;
+          }
           mbar_arrive_expect_tx(&sm.full[s], bytes);
 #if B200_EVICT_FIRST
           tma_bulk_g2s_hint(sm.stages + (size_t) s * stage_bytes, wbase + (size_t) k * cq * rp.R * 80, bytes, &sm.full[s], l2pol);

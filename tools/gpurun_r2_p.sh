@@ -10,3 +10,5 @@ done
 cat gpurun_out/r2p_probe.log
 B200_LIB=$PWD/llama.swift_b200/libb200_nomath.so timeout 300 python tools/phase_profile.py --layers 8 --pos 264 > gpurun_out/r2p_phase264_nomath.log 2>&1
 tail -24 gpurun_out/r2p_phase264_nomath.log
+B200_PROF_ATT=1 B200_LIB=$PWD/llama.swift_b200/libb200_profatt.so timeout 300 python tools/phase_profile.py --layers 8 --pos 264 > gpurun_out/r2p_phase264_att.log 2>&1
+tail -8 gpurun_out/r2p_phase264_att.log

@@ -62,5 +62,17 @@ for k, n in enumerate(names):
 print(f"{'sum of medians':>22}: {sum(np.median(seg[1:, k, :]) for k in range(NM)):.2f} us/layer")
 o = NM * nl
 print(f"output: wait {np.median(t[:, o + 1] - t[:, o]):.2f}  read+norm+quant {np.median(t[:, o + 2] - t[:, o + 1]):.2f}  rows {np.median(t[:, o + 3] - t[:, o + 2]):.2f}  store {np.median(t[:, o + 4] - t[:, o + 3]):.2f} us (median CTA)")
+if os.environ.get("B200_PROF_ATT") == "1":     # a -DB200_PROF_ATT=1 build: stamps inside the attention phase (CTAs that own a unit)
+    base = 18 * nl + 8
+    segs = ["wait for q/k/v of this token", "K.Q", "soft_max", "V.P chains"]
+    raw = buf[: ncta.value * marks].reshape(ncta.value, marks).astype(np.float64)
+    for k, n in enumerate(segs):
+        d = []
+        for il in range(1, nl):
+            a0, a1 = raw[:, base + 5 * il + k], raw[:, base + 5 * il + k + 1]
+            ok = (a0 > 0) & (a1 > 0)
+            d.append((a1[ok] - a0[ok]) / 1e3)
+        d = np.concatenate(d)
+        print(f"   attention / {n:>28}: median {np.median(d):5.2f} us   p90 {np.percentile(d, 90):5.2f} us   max {d.max():5.2f} us")
 if args.out:
     np.save(args.out, t)
