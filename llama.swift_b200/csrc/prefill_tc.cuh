@@ -32,6 +32,10 @@
 
 #include "ptx.cuh"
 
+#ifndef B200_TC_SKIP
+#define B200_TC_SKIP 0      // development ceilings (wrong results): 1 = epilogue without the fma chain, 2 = without the tcgen05.ld, 3 = A unpack without the conversion
+#endif
+
 namespace b200 {
 
 constexpr int TC_M = 128;                 // weight rows per tile = UMMA M = TMEM lanes
@@ -301,6 +305,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             uint32_t h[4];
+#if B200_TC_SKIP == 3
+            h[0] = ww[c]; h[1] = ww[c] >> 1; h[2] = ww[c] >> 2; h[3] = ww[c] >> 3;
+#else
 #pragma unroll
             for (int i = 0; i < 4; i++) {
               // byte i of the word: low nibble = element 2i, high nibble = element 2i+1 of this chunk.  0x6400 | x is the
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
               const __half2 r = __hfma2(*reinterpret_cast<const __half2 *>(&t), mulv, addv);
               h[i] = *reinterpret_cast<const uint32_t *>(&r);
             }
+#endif
             out4[c] = make_uint4(h[0], h[1], h[2], h[3]);
           }
           if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
@@ -355,11 +363,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
           mbar_wait(&tm_full[buf], (kb_g >> 1) & 1, limit);
           tc_fence_after();
           uint32_t d[32];                                  // 32 columns = this warp's 4 tokens x 8 lanes
+#if B200_TC_SKIP == 2
+#pragma unroll
+          for (int i = 0; i < 32; i++) d[i] = kb_g + i;
+#else
           tmem_ld32(tmem_base + t_lane + (uint32_t) buf * TC_N + (uint32_t) tg * (TH * 8), d);
           tmem_ld_wait();
+#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tm_empty[buf]);      // the accumulator buffer is free as soon as it is in registers
+#if B200_TC_SKIP == 1
+          acc[0][0] ^= (u64) d[0] ^ (u64) d[31];
+#else
 #pragma unroll
           for (int t = 0; t < TH; t++) {
             const float sdx = __fmul_rn(dw[b], dxv[t]);                                              // _mm256_mul_ps(d0, d1), ggml.c:1431
@@ -368,6 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
             for (int j = 0; j < 4; j++)
               acc[t][j] = ffma2(s2, pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
           }
+#endif
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[s]);
