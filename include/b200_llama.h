@@ -93,6 +93,9 @@ typedef struct b200_tokenizer b200_tokenizer;
 b200_tokenizer *b200_tokenizer_create(const b200_llama *m);      /* from the model's vocabulary (gpt_vocab, PO.mm:140-164) */
 b200_tokenizer *b200_tokenizer_create_from(const char *const *pieces, const int *lens, int n_vocab);
 void b200_tokenizer_free(b200_tokenizer *t);
+/* The model's own tokenizer, built on first use and kept with the handle (so a resident model, b200_llama_acquire, does not
+ * rebuild the ~90k-node trie of a 32000-piece vocabulary on every run).  Owned by the handle: do not free. */
+const b200_tokenizer *b200_llama_shared_tokenizer(b200_llama *m);
 int b200_llama_tokenize(const b200_tokenizer *t, const char *text, size_t text_len, int bos, int32_t *out, int cap);
 
 /* == llama_sample_top_p_top_k(vocab, logits, last_n_tokens, repeat_penalty, top_k, top_p, temp, rng),

@@ -313,6 +313,7 @@ struct b200_llama {
   // llama_hparams, PO.mm:41-50
   int n_vocab = 0, n_ctx = 0, n_embd = 0, n_mult = 0, n_head = 0, n_layer = 0, n_rot = 0, f16 = 0, n_ff = 0;
   std::vector<std::string> id_to_token;
+  b200_tokenizer *shared_tok = nullptr;    // built on first use, lives with the (resident) model: b200_llama_shared_tokenizer
 
   int device = 0, n_sm = 0;
   cudaStream_t stream = nullptr;
@@ -643,6 +644,7 @@ void free_model(b200_llama *m) {
   cudaFree(m->out.d_w); cudaFree(m->d_norm); cudaFree(m->d_tok_emb); cudaFree(m->d_k); cudaFree(m->d_v);
   cudaFree(m->d_rope); cudaFree(m->d_silu); cudaFree(m->d_exp);
   cudaFree(m->d_inpL); cudaFree(m->d_inpFF); cudaFree(m->d_q); cudaFree(m->d_att); cudaFree(m->d_h);   // d_logits lives inside d_xchg
+  if (m->shared_tok) b200_tokenizer_free(m->shared_tok);
   delete m->h_token_args; cudaFree(m->d_bar); cudaFree(m->d_am);
   cudaFree(m->b_x); cudaFree(m->b_ff); cudaFree(m->b_q); cudaFree(m->b_att); cudaFree(m->b_h); cudaFree(m->b_o); cudaFree(m->b_act); cudaFree(m->b_tok);
   cudaFree(m->b_xh); cudaFree(m->b_dxT);
@@ -1531,6 +1533,13 @@ int b200_llama_n_layer(const b200_llama *m) { return m->n_layer; }
 int b200_llama_n_head(const b200_llama *m) { return m->n_head; }
 int b200_llama_ftype(const b200_llama *m) { return m->f16; }
 
+const b200_tokenizer *b200_llama_shared_tokenizer(b200_llama *m) {
+  if (!m) return nullptr;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  if (!m->shared_tok) m->shared_tok = b200_tokenizer_create(m);
+  return m->shared_tok;
+}
+
 const char *b200_llama_token_str(const b200_llama *m, int id, int *len) {
   if (id < 0 || id >= m->n_vocab) { if (len) *len = 0; return ""; }
   if (len) *len = (int) m->id_to_token[id].size();
@@ -1668,6 +1677,15 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
   return rc;
 }
 
+
+#if B200_TC_TRACE
+/* development build only (-DB200_TC_TRACE=1): the hand-over timeline of CTA 0 of the last tcgen05 mat-mul launch */
+extern "C" int b200_debug_tc_trace(long long *out, int n_words) {
+  const size_t n = std::min<size_t>((size_t) n_words, 12 * 512) * sizeof(long long);
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, b200::g_tc_trace, n) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 /* out[N][M] = W[M x K] (Q4_0, ggml rows) x the N columns x[N][K], every column computed exactly as
  * ggml_compute_forward_mul_mat_q4_0_f32 does (ggml.c:6199-6222).  path 0: CUDA-core multi-column loop (weights streamed

@@ -147,10 +147,9 @@ int b200_llama_run(const char *model_path, const char *prompt, size_t prompt_len
   std::vector<const char *> pieces((size_t) n_vocab);
   std::vector<int> lens((size_t) n_vocab);
   for (int i = 0; i < n_vocab; i++) pieces[(size_t) i] = b200_llama_token_str(model, i, &lens[(size_t) i]);
-  b200_tokenizer *tok = b200_tokenizer_create_from(pieces.data(), lens.data(), n_vocab);
+  const b200_tokenizer *tok = b200_llama_shared_tokenizer(model);      // built once per resident model, not per run
   const int out = b200_llama_run_loop(eval_on_model, model, n_vocab, b200_llama_n_ctx(model), tok, pieces.data(), lens.data(), prompt,
                                       prompt_len, antiprompt, antiprompt_len, params, on_event, user);
-  b200_tokenizer_free(tok);
   b200_llama_release(model);                                                               // was ggml_free(model.ctx), PO.mm:900
   return out;
 }

@@ -11,8 +11,8 @@
 //     B  (32 x 8T)               column (token t, lane l) = token t's quantized activations at lane l's 4 positions, 0 elsewhere
 //     D  (128 x 8T, f32 in TMEM) = isum_l of every (row, token): products and 4-term sums of small integers are exact in
 //                                  f32, so D IS (float) isum -- no conversion step
-// and the epilogue warps drain D after EVERY block (TMEM is double-buffered: the MMA of block b+1 runs under the drain of
-// block b) and apply the reference's own per-lane fma chain in registers: 8 fma per (row, token, block), issued as 4
+// and the epilogue warps drain D after EVERY block (TMEM holds 4 accumulator tiles: the MMAs of the next blocks run under the drain
+// of block b) and apply the reference's own per-lane fma chain in registers: 8 fma per (row, token, block), issued as 4
 // fma.rn.f32x2.  That chain is the real cost of exact Q4_0 semantics (it is 2/3 of the CUDA-core decode loop as well); the
 // tensor cores remove everything else -- nibble handling per token, integer dot products, int -> float conversion.
 //
@@ -21,10 +21,10 @@
 //     warps 0-15  epilogue: thread = weight row = TMEM lane (four warps per lane quarter, 4 tokens each: one tcgen05.ld of 32
 //                 columns per block step and warp); 4 tokens x 8 lanes of f32 accumulators live in registers
 //     warp 16     TMA producer: per (item, quad of blocks) THREE cp.async.bulk boxes -- 10 KB of raw weights (4 blocks x 128
-//                 rows x 20 B), 4 KB of fp16 activations (16 tokens x 4 blocks), 256 B of block scales
+//                 rows x 20 B), 8 KB of zero-interleaved fp16 activations (16 tokens x 4 blocks), 256 B of block scales
 //     warp 17     MMA issuer (one elected lane; owns the TMEM allocation)
-//     warp 18     B builder: writes the 4 non-zero fp16 of every (token, lane) column; the zero pattern is written once
-//     warps 19-22 A unpacker: 16 nibble bytes -> 32 fp16 per row per block, straight into the UMMA canonical layout
+//     warps 18-21 operand producers: A = 16 nibble bytes -> 32 fp16 per row per block, straight into the UMMA canonical
+//                 layout; B = the 4 non-zero fp16 of every (token, lane) column (the zero pattern is written once)
 // Pipelines: raw ring (TMA <-> unpack/epilogue), operand buffers (unpack/build <-> MMA via tcgen05.commit), TMEM
 // accumulators (MMA <-> epilogue).  All mbarrier based; no __syncthreads in steady state.
 #pragma once
@@ -32,25 +32,23 @@
 
 #include "ptx.cuh"
 
-#ifndef B200_TC_SKIP
-#define B200_TC_SKIP 0      // development ceilings (wrong results): 1 = epilogue without the fma chain, 2 = without the tcgen05.ld, 3 = A unpack without the conversion
-#endif
-
 namespace b200 {
 
 constexpr int TC_M = 128;                 // weight rows per tile = UMMA M = TMEM lanes
 constexpr int TC_T = 16;                  // tokens per tile
 constexpr int TC_N = TC_T * 8;            // UMMA N: (token, lane) columns
 constexpr int TC_EPI_WARPS = 16;          // epilogue warps: 4 per TMEM lane quarter, 4 tokens each
-constexpr int TC_THREADS = (TC_EPI_WARPS + 7) * 32;   // + TMA, MMA, B builder, 4 unpack warps
+constexpr int TC_THREADS = (TC_EPI_WARPS + 6) * 32;   // + TMA, MMA, 4 operand-producer warps
 constexpr int TC_RAW_STAGES = 3;
+constexpr int TC_NBUF = 4;                // TMEM accumulator buffers (4 x 128 columns = all of TMEM)
+constexpr int TC_ABUF = 8;                // operand buffers (A, B): two quads of blocks, so that the producers fence ONCE per quad
 constexpr int TC_QUAD_BYTES = TC_M * 80;  // 4 blocks x 128 rows x 20 B
 constexpr int TC_A_BYTES = TC_M * 64;     // 128 rows x 32 fp16
 constexpr int TC_B_BYTES = TC_N * 64;     // 128 columns x 32 fp16
 constexpr int TC_DX_BYTES = 4 * TC_T * 4; // block scales of the 16 tokens, 4 blocks
-constexpr int TC_XH_BYTES = TC_T * 4 * 64; // fp16 activations of the 16 tokens, 4 blocks
+constexpr int TC_XH_BYTES = TC_T * 4 * 128; // fp16 activations of the 16 tokens, 4 blocks, zero-interleaved (8 B per (lane, half))
 constexpr int TC_STAGE_BYTES = TC_QUAD_BYTES + TC_XH_BYTES + TC_DX_BYTES;
-constexpr int TC_SMEM = TC_RAW_STAGES * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES + 256;
+constexpr int TC_SMEM = TC_RAW_STAGES * TC_STAGE_BYTES + TC_ABUF * (TC_A_BYTES + TC_B_BYTES) + 512;
 
 // ---- prefill weight layout: [row tile mt][quad q] -> { [block b < 4][row r < 128][16 raw nibble bytes] | [row][4] f32 d } ---------
 __host__ __device__ __forceinline__ size_t tc_weight_bytes(int M, int nb) {
@@ -80,7 +78,10 @@ __global__ void repack_prefill_kernel(const uint8_t *src, uint8_t *dst, int M, i
 
 // ---- activation operand: fp16 copy of the quantized activations + block scales, one contiguous box per (token tile, quad) ----
 // from batch_prep_kernel's planes (act):
-//   xh  [token tile nt][quad q][token t < 16][block b < 4][32] half   (values -7..7; tokens >= N and blocks >= nb are zero)
+//   xh  [token tile nt][quad q][token t < 16][block b < 4][half h < 2][lane l < 8] 8 bytes
+//       = the two elements {2l, 2l+1} (h = 0) or {16+2l, 17+2l} (h = 1) of AVX lane l, already in the form the block-diagonal
+//       operand wants them: (x_a, 0, x_b, 0) for l % 4 < 2, (0, x_a, 0, x_b) otherwise (see the K order of the A unpacker);
+//       values -127..127, tokens >= N and blocks >= nb are zero
 //   dxq [token tile nt][quad q][block b < 4][token t < 16]     float
 __global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __half *xh, float *dxq, int nb, int N, int Npad) {
   const int n = blockIdx.y;
@@ -88,11 +89,11 @@ __global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __hal
   const int nbq = (nb + 3) >> 2, nbp = nbq * 4;
   if (b >= nbp) return;
   const int nt = n / TC_T, t = n % TC_T, q = b >> 2, bq = b & 3;
-  __half2 *dst = reinterpret_cast<__half2 *>(xh + ((((size_t) nt * nbq + q) * TC_T + t) * 4 + bq) * 32);
+  uint2 *dst = reinterpret_cast<uint2 *>(xh + ((((size_t) nt * nbq + q) * TC_T + t) * 4 + bq) * 64);     // [h][l]
   float *dd = dxq + (((size_t) nt * nbq + q) * 4 + bq) * TC_T + t;
   if (n >= N || b >= nb) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) dst[i] = __floats2half2_rn(0.0f, 0.0f);
+    for (int i = 0; i < 16; i++) dst[i] = make_uint2(0u, 0u);
     *dd = 0.0f;
     return;
   }
@@ -106,10 +107,12 @@ __global__ void batch_act_tc_kernel(const uint8_t *act, size_t act_stride, __hal
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const int l = 2 * p + s;
-      const int e0 = (int) (int8_t) (lw[s] & 0xff), e1 = (int) (int8_t) ((lw[s] >> 8) & 0xff);
-      const int e2 = (int) (int8_t) ((lw[s] >> 16) & 0xff), e3 = (int) (int8_t) (lw[s] >> 24);
-      dst[l] = __floats2half2_rn((float) e0, (float) e1);            // elements 2l, 2l+1
-      dst[8 + l] = __floats2half2_rn((float) e2, (float) e3);        // elements 16+2l, 17+2l
+      const int sh = (l & 2) ? 16 : 0;                 // odd K positions for l % 4 >= 2
+      uint32_t e[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) e[i] = (uint32_t) __half_as_ushort(__float2half((float) (int) (int8_t) ((lw[s] >> (8 * i)) & 0xff))) << sh;
+      dst[l] = make_uint2(e[0], e[1]);                 // elements 2l, 2l+1
+      dst[8 + l] = make_uint2(e[2], e[3]);             // elements 16+2l, 17+2l
     }
   }
   *dd = dxs[b];
@@ -165,6 +168,87 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- lean shared-memory / mbarrier forms on 32-bit shared addresses (the hot loops keep ONE base register) ----------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// try_wait with a suspend-time hint: the warp sleeps in the barrier unit (SASS: TRYWAIT, NANOSLEEP.SYNCS, PHASECHK) instead of
+// polling through issue slots the critical warps need.  Measured: on EVERY role it is slower than polling (the wake-up adds
+// latency to each hand-over: 2-layer 256-token probe 4.22 ms against 3.85 ms), so only roles with slack use it (SLEEP = true).
+__device__ __forceinline__ bool mbar_try_wait_sleep_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+// bounded wait (see mbar_wait in ptx.cuh) that looks at the clock only every 16th wake-up
+template <bool SLEEP = false>
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, long long limit) {
+  if (mbar_try_wait_a(bar, parity)) return true;
+  long long t0 = 0;
+  for (uint32_t n = 1; !(SLEEP ? mbar_try_wait_sleep_a(bar, parity, 1000u) : mbar_try_wait_a(bar, parity)); n++) {
+    if ((n & 15u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (wait_give_up(t0, limit)) return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Development switch: B200_TC_TRACE=1 stamps clock64() at the hand-over points of CTA 0's first 512 block steps into
+// g_tc_trace (read back with b200_debug_tc_trace); tools/tc_trace.py turns it into a per-role timeline.
+#ifndef B200_TC_EPI_SLEEP
+#define B200_TC_EPI_SLEEP 1     // the epilogue warps' accumulator wait: 1 = sleeping try_wait, 0 = polling
+#endif
+#ifndef B200_TC_LD16
+#define B200_TC_LD16 1          // epilogue: two tcgen05.ld x16 per block step instead of one x32
+#endif
+#ifndef B200_TC_TRACE
+#define B200_TC_TRACE 0
+#endif
+#if B200_TC_TRACE
+__device__ long long g_tc_trace[12][512];
+#define TC_STAMP(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512u) g_tc_trace[slot][idx] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot, idx) do { } while (0)
+#endif
+
 struct GemmTcArgs {
   const uint8_t *w;        // prefill weight layout (repack_prefill_kernel)
   int M, nb;
@@ -184,152 +268,159 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
   const int n_items = n_mt * n_nt;
 
   uint8_t *raw = smem;                                                       // [TC_RAW_STAGES][weights quad | xh | dx]
-  uint8_t *abuf = smem + TC_RAW_STAGES * TC_STAGE_BYTES;                      // [2][TC_A_BYTES]
-  uint8_t *bbuf = abuf + 2 * TC_A_BYTES;                                      // [2][TC_B_BYTES]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bbuf + 2 * TC_B_BYTES);
+  uint8_t *abuf = smem + TC_RAW_STAGES * TC_STAGE_BYTES;                      // [TC_ABUF][TC_A_BYTES]
+  uint8_t *bbuf = abuf + TC_ABUF * TC_A_BYTES;                                // [TC_ABUF][TC_B_BYTES]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bbuf + TC_ABUF * TC_B_BYTES);
   uint64_t *raw_full = bars, *raw_empty = bars + TC_RAW_STAGES;               // TMA <-> unpack / build / epilogue
-  uint64_t *ab_full = bars + 2 * TC_RAW_STAGES, *ab_empty = ab_full + 2;      // unpack + build <-> MMA
-  uint64_t *tm_full = ab_empty + 2, *tm_empty = tm_full + 2;                  // MMA <-> epilogue
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
+  uint64_t *ab_full = bars + 2 * TC_RAW_STAGES, *ab_empty = ab_full + TC_ABUF;   // unpack + build <-> MMA
+  uint64_t *tm_full = ab_empty + TC_ABUF, *tm_empty = tm_full + TC_NBUF;      // MMA <-> epilogue
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + TC_NBUF);
 
   if (tid == 0) {
-    for (int s = 0; s < TC_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TC_EPI_WARPS + 5); }   // epilogue warps + B builder + 4 unpack warps
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&ab_full[i], 5);       // 4 unpack warps + the B builder
+    for (int s = 0; s < TC_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TC_EPI_WARPS + 4); }   // epilogue warps + 4 producer warps
+    for (int i = 0; i < TC_ABUF; i++) {
+      mbar_init(&ab_full[i], 4);       // the 4 producer warps
       mbar_init(&ab_empty[i], 1);      // tcgen05.commit
+    }
+    for (int i = 0; i < TC_NBUF; i++) {
       mbar_init(&tm_full[i], 1);       // tcgen05.commit
       mbar_init(&tm_empty[i], TC_EPI_WARPS);   // the epilogue warps
     }
     fence_mbar_init();
   }
   // the zero pattern of the block-diagonal operand is written once; only the non-zero positions are rewritten per block
-  for (int i = tid; i < 2 * TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(bbuf)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < TC_ABUF * TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(bbuf)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
-  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, 256);      // 2 accumulator buffers of 128 columns
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, TC_NBUF * TC_N);      // TC_NBUF accumulator buffers of 128 columns (all 512 TMEM columns)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long limit = a.spin_limit;
+  // Everything below addresses the barriers as 32-bit shared addresses off ONE base register (immediate offsets in the
+  // SASS), and walks the rings with running (stage, parity) counters: the first version of this kernel spent most of its
+  // issue slots on re-derived addresses, g % 3 divisions and 14-instruction polling loops (profiles/r2_v_tc_timeline.md).
+  const uint32_t bar0 = smem_u32(bars);
+  constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 8 * TC_RAW_STAGES, AB_FULL = 16 * TC_RAW_STAGES, AB_EMPTY = AB_FULL + 8 * TC_ABUF;
+  constexpr uint32_t TM_FULL = AB_EMPTY + 8 * TC_ABUF, TM_EMPTY = TM_FULL + 8 * TC_NBUF;
+  static_assert(TC_NBUF == 4 && TC_ABUF == 8, "a quad of blocks = one round of the TMEM ring = half a round of the operand ring");
 
   if (warp == TC_EPI_WARPS) {
-    // ===== TMA producer: three boxes per (item, quad) -- 10 KB of weights, 4 KB of fp16 activations, 256 B of block scales =====
+    // ===== TMA producer: three boxes per (item, quad) -- 10 KB of weights, 8 KB of fp16 activations, 256 B of block scales =====
     if (lane == 0) {
+      uint32_t rs = 0, rpar = 1;           // raw ring: stage, parity of the EMPTY barrier to wait for (first round: passes)
       uint32_t g = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = item / n_nt, nt = item % n_nt;
+        const uint8_t *wsrc = a.w + (size_t) mt * nbq * TC_QUAD_BYTES;
+        const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(a.xh) + (size_t) nt * nbq * TC_XH_BYTES;
+        const uint8_t *dsrc = reinterpret_cast<const uint8_t *>(a.dxT) + (size_t) nt * nbq * TC_DX_BYTES;
         for (int q = 0; q < nbq; q++, g++) {
-          const int s = g % TC_RAW_STAGES;
-          if (g >= TC_RAW_STAGES && !mbar_wait(&raw_empty[s], ((g / TC_RAW_STAGES) - 1) & 1, limit)) { item = n_items; break; }   // abandoned: stop issuing
-          uint8_t *dst = raw + (size_t) s * TC_STAGE_BYTES;
-          mbar_arrive_expect_tx(&raw_full[s], TC_STAGE_BYTES);
-          tma_bulk_g2s(dst, a.w + ((size_t) mt * nbq + q) * TC_QUAD_BYTES, TC_QUAD_BYTES, &raw_full[s]);
-          tma_bulk_g2s(dst + TC_QUAD_BYTES, reinterpret_cast<const uint8_t *>(a.xh) + ((size_t) nt * nbq + q) * TC_XH_BYTES, TC_XH_BYTES, &raw_full[s]);
-          tma_bulk_g2s(dst + TC_QUAD_BYTES + TC_XH_BYTES, reinterpret_cast<const uint8_t *>(a.dxT) + ((size_t) nt * nbq + q) * TC_DX_BYTES, TC_DX_BYTES, &raw_full[s]);
+          if (g >= TC_RAW_STAGES && !mbar_wait_a<true>(bar0 + RAW_EMPTY + 8 * rs, rpar, limit)) { item = n_items; break; }   // abandoned: stop issuing
+          uint8_t *dst = raw + (size_t) rs * TC_STAGE_BYTES;
+          uint64_t *full = raw_full + rs;
+          TC_STAMP(0, g);
+          mbar_arrive_expect_tx(full, TC_STAGE_BYTES);
+          tma_bulk_g2s(dst, wsrc + (size_t) q * TC_QUAD_BYTES, TC_QUAD_BYTES, full);
+          tma_bulk_g2s(dst + TC_QUAD_BYTES, xsrc + (size_t) q * TC_XH_BYTES, TC_XH_BYTES, full);
+          tma_bulk_g2s(dst + TC_QUAD_BYTES + TC_XH_BYTES, dsrc + (size_t) q * TC_DX_BYTES, TC_DX_BYTES, full);
+          if (++rs == TC_RAW_STAGES) { rs = 0; rpar ^= 1; }
         }
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = f16, both K-major, N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t) (TC_N >> 3) << 17) | ((uint32_t) (TC_M >> 4) << 24);
-      uint32_t kb_g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int kb = 0; kb < nbq * 4; kb++, kb_g++) {
-          const int buf = kb_g & 1;
-          const uint32_t par = (kb_g >> 1) & 1;
-          if (!mbar_wait(&ab_full[buf], par, limit) || (kb_g >= 2 && !mbar_wait(&tm_empty[buf], ((kb_g >> 1) - 1) & 1, limit))) { item = n_items; break; }
+    // ===== MMA issuer: the whole warp walks the loop converged and ONE elected lane issues (no divergent-uniform fix-up code) =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = f16, both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t) (TC_N >> 3) << 17) | ((uint32_t) (TC_M >> 4) << 24);
+    // K = 32 elements = 4 chunks of 16 bytes per row; one MMA consumes 2 chunks (K = 16 fp16).  Descriptors differ only in the
+    // 14-bit address field: + buffer * 512 (8 KB), + 256 for the second pair of chunks
+    const uint64_t a_desc0 = umma_desc(smem_u32(abuf), TC_M * 16, 128), b_desc0 = umma_desc(smem_u32(bbuf), TC_N * 16, 128);
+    const bool leader = elect_one_sync();
+    uint32_t qg = 0;                      // quads so far: operand half = qg & 1, parities from qg
+    bool alive = true;
+    for (int item = blockIdx.x; item < n_items && alive; item += gridDim.x) {
+      for (int q = 0; q < nbq && alive; q++, qg++) {
+        const uint32_t half = (qg & 1) * 4;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const uint32_t buf = half + b;
+          if (!mbar_wait_a(bar0 + AB_FULL + 8 * buf, (qg >> 1) & 1, limit)) { alive = false; break; }
+          TC_STAMP(4, qg * 4 + b);
+          if (qg >= 1 && !mbar_wait_a(bar0 + TM_EMPTY + 8 * b, (qg - 1) & 1, limit)) { alive = false; break; }
+          TC_STAMP(5, qg * 4 + b);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(abuf + buf * TC_A_BYTES), b_addr = smem_u32(bbuf + buf * TC_B_BYTES);
-          const uint32_t d_tmem = tmem_base + (uint32_t) buf * TC_N;
-          // K = 32 elements = 4 chunks of 16 bytes per row; one MMA consumes 2 chunks (K = 16 fp16)
-          umma_f16(d_tmem, umma_desc(a_addr, TC_M * 16, 128), umma_desc(b_addr, TC_N * 16, 128), idesc, 0u);
-          umma_f16(d_tmem, umma_desc(a_addr + 2 * TC_M * 16, TC_M * 16, 128), umma_desc(b_addr + 2 * TC_N * 16, TC_N * 16, 128), idesc, 1u);
-          umma_commit(&ab_empty[buf]);      // operand buffers free once both MMAs have read them
-          umma_commit(&tm_full[buf]);       // accumulators complete
-        }
-      }
-    }
-  } else if (warp == TC_EPI_WARPS + 2) {
-    // ===== B builder: column (t, l) of block kb gets token t's activations at elements 2l, 2l+1 (K chunk l/4) and 16+2l, 17+2l
-    // (K chunk 2 + l/4), read from the staged fp16 copy; every lane handles 4 (t, l) pairs =====
-    uint32_t g = 0, kb_g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      for (int q = 0; q < nbq; q++, g++) {
-        const int s = g % TC_RAW_STAGES;
-        mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
-        const uint32_t *xs = reinterpret_cast<const uint32_t *>(raw + (size_t) s * TC_STAGE_BYTES + TC_QUAD_BYTES);   // [t][b][16 words]
-        for (int b = 0; b < 4; b++, kb_g++) {
-          const int buf = kb_g & 1;
-          uint32_t v0[4], v1[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int i = lane + 32 * j, t = i >> 3, l = i & 7;
-            v0[j] = xs[(t * 4 + b) * 16 + l];
-            v1[j] = xs[(t * 4 + b) * 16 + 8 + l];
+          if (leader) {
+            const uint64_t ad = a_desc0 + (uint64_t) (buf * (TC_A_BYTES >> 4)), bd = b_desc0 + (uint64_t) (buf * (TC_B_BYTES >> 4));
+            const uint32_t d_tmem = tmem_base + (uint32_t) b * TC_N;
+            umma_f16(d_tmem, ad, bd, idesc, 0u);
+            umma_f16(d_tmem, ad + (2 * TC_M * 16 >> 4), bd + (2 * TC_N * 16 >> 4), idesc, 1u);
+            umma_commit_a(bar0 + AB_EMPTY + 8 * buf);      // operand buffers free once both MMAs have read them
+            umma_commit_a(bar0 + TM_FULL + 8 * b);         // accumulators complete
           }
-          if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
-          uint8_t *B = bbuf + buf * TC_B_BYTES;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int i = lane + 32 * j, t = i >> 3, l = i & 7;
-            uint8_t *p = B + (l >> 2) * (TC_N * 16) + t * 128 + l * 16 + 4 * (l & 3);
-            *reinterpret_cast<uint32_t *>(p) = v0[j];
-            *reinterpret_cast<uint32_t *>(p + 2 * TC_N * 16) = v1[j];
-          }
-          fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ab_full[buf]);
+          TC_STAMP(6, qg * 4 + b);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);
       }
     }
-  } else if (warp >= TC_EPI_WARPS + 3) {
-    // ===== A unpacker: thread = weight row; 16 nibble bytes -> 32 fp16 (q - 8), chunk c = elements 8c..8c+7 = nibble word c =====
-    const int row = (warp - (TC_EPI_WARPS + 3)) * 32 + lane;
-    uint32_t g = 0, kb_g = 0;
-    const __half2 mulv = __halves2half2(__float2half(1.0f), __float2half(0.0625f));
-    const __half2 addv = __halves2half2(__float2half(-1032.0f), __float2half(-72.0f));
+  } else if (warp >= TC_EPI_WARPS + 2) {
+    // ===== operand producers (4 warps).  A: thread = weight row; 16 nibble bytes -> 32 fp16 (q - 8) straight into the UMMA
+    // canonical layout.  Any K order is allowed INSIDE an AVX lane's four elements as long as B uses the same one, which buys a
+    // 9-instruction unpack per nibble word (SHF, 4 LOP3, 4 HFMA2): chunk c (elements 8c..8c+7 = nibble word c) is stored in the
+    // order 0 4 1 5 2 6 3 7 -- (w & 0x000F000F) | 0x6400.. is the fp16 pair (1024 + e0, 1024 + e4), (w & 0x00F000F0) | 0x6400..
+    // the pair (1024 + 16 e1, 1024 + 16 e5), and the same on w >> 8 for (e2, e6), (e3, e7).
+    // B: lane = one (token, AVX lane) column of this warp's 4 tokens; its two non-zero 8-byte slots per block come zero-interleaved
+    // from batch_act_tc_kernel, so the builder is two LDS.64 + two STS.64. =====
+    const int pw = warp - (TC_EPI_WARPS + 2);
+    const int row = pw * 32 + lane;
+    uint32_t rs = 0, rpar = 0, qg = 0;
+    const __half2 mul1 = __float2half2_rn(1.0f), add1 = __float2half2_rn(-1032.0f);
+    const __half2 mul16 = __float2half2_rn(0.0625f), add16 = __float2half2_rn(-72.0f);
+    const uint32_t raw0 = smem_u32(raw) + row * 16, a0 = smem_u32(abuf) + (row >> 3) * 128 + (row & 7) * 16;
+    const uint32_t bl = lane & 7, bt = pw * 4 + (lane >> 3);            // column n = bt * 8 + bl
+    const uint32_t xs0 = smem_u32(raw) + TC_QUAD_BYTES + bt * 512 + bl * 8;                                  // + b * 128, + 64 for h = 1
+    const uint32_t b0 = smem_u32(bbuf) + (bl >> 2) * (TC_N * 16) + (bt * 8 + bl) * 16 + 8 * (bl & 1);        // + 2 * TC_N * 16 for h = 1
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      for (int q = 0; q < nbq; q++, g++) {
-        const int s = g % TC_RAW_STAGES;
-        mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
-        const uint8_t *st = raw + (size_t) s * TC_STAGE_BYTES;
-        for (int b = 0; b < 4; b++, kb_g++) {
-          const int buf = kb_g & 1;
-          const uint4 nib = *reinterpret_cast<const uint4 *>(st + (size_t) b * TC_M * 16 + row * 16);
+      for (int q = 0; q < nbq; q++, qg++) {
+        mbar_wait_a(bar0 + RAW_FULL + 8 * rs, rpar, limit);
+        if (row == 0) TC_STAMP(1, qg);
+        const uint32_t st = raw0 + rs * TC_STAGE_BYTES, xs = xs0 + rs * TC_STAGE_BYTES;
+        const uint32_t half = (qg & 1) * 4;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const uint4 nib = lds_u128(st + b * TC_M * 16);
+          const uint2 x0 = lds_u64(xs + b * 128), x1 = lds_u64(xs + b * 128 + 64);
           const uint32_t ww[4] = {nib.x, nib.y, nib.z, nib.w};
           uint4 out4[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            uint32_t h[4];
-#if B200_TC_SKIP == 3
-            h[0] = ww[c]; h[1] = ww[c] >> 1; h[2] = ww[c] >> 2; h[3] = ww[c] >> 3;
-#else
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              // byte i of the word: low nibble = element 2i, high nibble = element 2i+1 of this chunk.  0x6400 | x is the
-              // fp16 1024 + x: low half 1024 + lo, high half 1024 + 16 hi; (x * {1, 1/16}) + {-1032, -72} = {lo - 8, hi - 8}
-              const uint32_t by = prmt(ww[c], 0u, 0x4040u | (uint32_t) i | ((uint32_t) i << 8));      // 0x00BB00BB
-              const uint32_t t = (by & 0x00F0000Fu) | 0x64006400u;
-              const __half2 r = __hfma2(*reinterpret_cast<const __half2 *>(&t), mulv, addv);
-              h[i] = *reinterpret_cast<const uint32_t *>(&r);
-            }
-#endif
-            out4[c] = make_uint4(h[0], h[1], h[2], h[3]);
+            const uint32_t w = ww[c], w8 = w >> 8;
+            const uint32_t ta = (w & 0x000F000Fu) | 0x64006400u, tb = (w & 0x00F000F0u) | 0x64006400u;
+            const uint32_t tc = (w8 & 0x000F000Fu) | 0x64006400u, td = (w8 & 0x00F000F0u) | 0x64006400u;
+            const __half2 ra = __hfma2(*reinterpret_cast<const __half2 *>(&ta), mul1, add1);
+            const __half2 rb = __hfma2(*reinterpret_cast<const __half2 *>(&tb), mul16, add16);
+            const __half2 rc = __hfma2(*reinterpret_cast<const __half2 *>(&tc), mul1, add1);
+            const __half2 rd = __hfma2(*reinterpret_cast<const __half2 *>(&td), mul16, add16);
+            out4[c] = make_uint4(*reinterpret_cast<const uint32_t *>(&ra), *reinterpret_cast<const uint32_t *>(&rb),
+                                 *reinterpret_cast<const uint32_t *>(&rc), *reinterpret_cast<const uint32_t *>(&rd));
           }
-          if (kb_g >= 2) mbar_wait(&ab_empty[buf], ((kb_g >> 1) - 1) & 1, limit);
-          uint8_t *A = abuf + buf * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+          if (qg >= 2) mbar_wait_a(bar0 + AB_EMPTY + 8 * (half + b), ((qg >> 1) - 1) & 1, limit);
+          const uint32_t A = a0 + (half + b) * TC_A_BYTES;
 #pragma unroll
-          for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(A + c * (TC_M * 16)) = out4[c];
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ab_full[buf]);
+          for (int c = 0; c < 4; c++) sts_u128(A + c * (TC_M * 16), out4[c]);
+          const uint32_t B = b0 + (half + b) * TC_B_BYTES;
+          sts_u64(B, x0);
+          sts_u64(B + 2 * TC_N * 16, x1);
         }
+        if (row == 0) TC_STAMP(2, qg);
+        fence_proxy_async_smem();          // ONE generic -> async proxy fence for the quad's 4 operand buffers
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);
+        if (row == 0) TC_STAMP(3, qg);
+        if (lane == 0) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) mbar_arrive_a(bar0 + AB_FULL + 8 * (half + b));
+          mbar_arrive_a(bar0 + RAW_EMPTY + 8 * rs);
+        }
+        if (++rs == TC_RAW_STAGES) { rs = 0; rpar ^= 1; }
       }
     }
   } else {
@@ -339,8 +430,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
     static_assert(TH * 8 == 32, "one 32-column tcgen05.ld per block step and warp");
     const int wq = warp & 3, tg = warp >> 2;
     const int row = wq * 32 + lane;
-    const uint32_t t_lane = ((uint32_t) (wq * 32)) << 16;
-    uint32_t g = 0, kb_g = 0;
+    const uint32_t taddr0 = tmem_base + (((uint32_t) (wq * 32)) << 16) + (uint32_t) tg * (TH * 8);
+    const uint32_t dw0 = smem_u32(raw) + 4 * TC_M * 16 + row * 16, dx0 = smem_u32(raw) + TC_QUAD_BYTES + TC_XH_BYTES + tg * TH * 4;
+    uint32_t rs = 0, rpar = 0, qg = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / n_nt, nt = item % n_nt;
       u64 acc[TH][4];
@@ -348,46 +440,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
       for (int t = 0; t < TH; t++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[t][j] = pack_f2(0.0f, 0.0f);
-      for (int q = 0; q < nbq; q++, g++) {
-        const int s = g % TC_RAW_STAGES;
-        mbar_wait(&raw_full[s], (g / TC_RAW_STAGES) & 1, limit);
-        const uint8_t *st = raw + (size_t) s * TC_STAGE_BYTES;
-        const float4 dw4 = *reinterpret_cast<const float4 *>(st + (size_t) 4 * TC_M * 16 + row * 16);
-        const float dw[4] = {dw4.x, dw4.y, dw4.z, dw4.w};
-        const float *dxq = reinterpret_cast<const float *>(st + TC_QUAD_BYTES + TC_XH_BYTES) + tg * TH;
+      for (int q = 0; q < nbq; q++, qg++) {
+        mbar_wait_a<true>(bar0 + RAW_FULL + 8 * rs, rpar, limit);
+        const uint32_t so = rs * TC_STAGE_BYTES;
 #pragma unroll
-        for (int b = 0; b < 4; b++, kb_g++) {
-          const int buf = kb_g & 1;
-          const float4 dx4 = *reinterpret_cast<const float4 *>(dxq + b * TC_T);
-          const float dxv[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
-          mbar_wait(&tm_full[buf], (kb_g >> 1) & 1, limit);
+        for (int b = 0; b < 4; b++) {
+          // d_w * d_x of this block for the warp's 4 tokens, before the accumulators arrive (the scales die here)
+          const float dwb = lds_f32(dw0 + so + 4 * b);
+          const float4 dx4 = lds_f32x4(dx0 + so + b * TC_T * 4);
+          u64 s2[TH];
+          {
+            const float s0 = __fmul_rn(dwb, dx4.x), s1 = __fmul_rn(dwb, dx4.y), s2f = __fmul_rn(dwb, dx4.z), s3 = __fmul_rn(dwb, dx4.w);   // _mm256_mul_ps(d0, d1), ggml.c:1431
+            s2[0] = pack_f2(s0, s0); s2[1] = pack_f2(s1, s1); s2[2] = pack_f2(s2f, s2f); s2[3] = pack_f2(s3, s3);
+          }
+          if (threadIdx.x == 0) TC_STAMP(10, qg * 4 + b);
+          mbar_wait_a<B200_TC_EPI_SLEEP != 0>(bar0 + TM_FULL + 8 * b, qg & 1, limit);
+          if (threadIdx.x == 0) TC_STAMP(7, qg * 4 + b);
           tc_fence_after();
-          uint32_t d[32];                                  // 32 columns = this warp's 4 tokens x 8 lanes
-#if B200_TC_SKIP == 2
-#pragma unroll
-          for (int i = 0; i < 32; i++) d[i] = kb_g + i;
-#else
-          tmem_ld32(tmem_base + t_lane + (uint32_t) buf * TC_N + (uint32_t) tg * (TH * 8), d);
+#if B200_TC_LD16
+          // two 16-column loads: half the live registers of one 32-column load, which lets the compiler keep the loop's
+          // addresses in registers under the 80-register cap of 704 threads
+          uint32_t d[16];
+          tmem_ld16(taddr0 + (uint32_t) b * TC_N, d);
           tmem_ld_wait();
-#endif
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tm_empty[buf]);      // the accumulator buffer is free as soon as it is in registers
-#if B200_TC_SKIP == 1
-          acc[0][0] ^= (u64) d[0] ^ (u64) d[31];
-#else
 #pragma unroll
-          for (int t = 0; t < TH; t++) {
-            const float sdx = __fmul_rn(dw[b], dxv[t]);                                              // _mm256_mul_ps(d0, d1), ggml.c:1431
-            const u64 s2 = pack_f2(sdx, sdx);
+          for (int t = 0; t < 2; t++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
-              acc[t][j] = ffma2(s2, pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
-          }
+              acc[t][j] = ffma2(s2[t], pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+          tmem_ld16(taddr0 + (uint32_t) b * TC_N + 16u, d);
+          tmem_ld_wait();
+          if (threadIdx.x == 0) TC_STAMP(8, qg * 4 + b);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
+#pragma unroll
+          for (int t = 2; t < 4; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              acc[t][j] = ffma2(s2[t], pack_i2((int) d[(t - 2) * 8 + 2 * j], (int) d[(t - 2) * 8 + 2 * j + 1]), acc[t][j]);
+#else
+          uint32_t d[32];                                  // 32 columns = this warp's 4 tokens x 8 lanes
+          tmem_ld32(taddr0 + (uint32_t) b * TC_N, d);
+          tmem_ld_wait();
+          if (threadIdx.x == 0) TC_STAMP(8, qg * 4 + b);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
+#pragma unroll
+          for (int t = 0; t < TH; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              acc[t][j] = ffma2(s2[t], pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
 #endif
         }
+        if (threadIdx.x == 0) TC_STAMP(9, qg);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);
+        if (lane == 0) mbar_arrive_a(bar0 + RAW_EMPTY + 8 * rs);
+        if (++rs == TC_RAW_STAGES) { rs = 0; rpar ^= 1; }
       }
       // horizontal sum exactly as ggml.c:1461-1466: (acc[k] + acc[k+4]) k < 4, then (r0 + r2) + (r1 + r3)
       const int grow = mt * TC_M + row;
@@ -408,7 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
   __syncthreads();
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, TC_NBUF * TC_N);
   }
 }
 
