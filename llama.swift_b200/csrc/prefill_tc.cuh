@@ -196,6 +196,18 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe.  (Experiment, not in the product: issuing the TMA copies from the MMA warp's loop by polling the ring --
+// 21 warps instead of 22 -- was 10x slower with try_wait as the poll, which suspends the thread for a system-dependent time
+// when the phase is not complete, and still 28% slower with test_wait: the MMA warp is the one role with no slack.)
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // try_wait with a suspend-time hint: the warp sleeps in the barrier unit (SASS: TRYWAIT, NANOSLEEP.SYNCS, PHASECHK) instead of
 // polling through issue slots the critical warps need.  Measured: on EVERY role it is slower than polling (the wake-up adds
 // latency to each hand-over: 2-layer 256-token probe 4.22 ms against 3.85 ms), so only roles with slack use it (SLEEP = true).
@@ -237,7 +249,7 @@ __device__ __forceinline__ bool elect_one_sync() {
 #define B200_TC_EPI_SLEEP 1     // the epilogue warps' accumulator wait: 1 = sleeping try_wait, 0 = polling
 #endif
 #ifndef B200_TC_LD16
-#define B200_TC_LD16 1          // epilogue: two tcgen05.ld x16 per block step instead of one x32
+#define B200_TC_LD16 0          // epilogue: 1 = two tcgen05.ld x16 per block step instead of one x32 (measured: 3.73 ms against 3.61 ms on the 2-layer probe)
 #endif
 #ifndef B200_TC_TRACE
 #define B200_TC_TRACE 0
@@ -430,8 +442,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
     static_assert(TH * 8 == 32, "one 32-column tcgen05.ld per block step and warp");
     const int wq = warp & 3, tg = warp >> 2;
     const int row = wq * 32 + lane;
-    const uint32_t taddr0 = tmem_base + (((uint32_t) (wq * 32)) << 16) + (uint32_t) tg * (TH * 8);
-    const uint32_t dw0 = smem_u32(raw) + 4 * TC_M * 16 + row * 16, dx0 = smem_u32(raw) + TC_QUAD_BYTES + TC_XH_BYTES + tg * TH * 4;
+    uint32_t taddr0 = tmem_base + (((uint32_t) (wq * 32)) << 16) + (uint32_t) tg * (TH * 8);
+    uint32_t dw0 = smem_u32(raw) + 4 * TC_M * 16 + row * 16, dx0 = smem_u32(raw) + TC_QUAD_BYTES + TC_XH_BYTES + tg * TH * 4;
+    // opaque to the compiler: under the 80-register cap it otherwise re-derives these from %tid (S2R + dependent ALU, ~25
+    // cycles of exposed latency each) in every block step
+    asm volatile("" : "+r"(taddr0), "+r"(dw0), "+r"(dx0));
     uint32_t rs = 0, rpar = 0, qg = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / n_nt, nt = item % n_nt;
@@ -443,60 +458,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) q4_gemm_tc_kernel(const GemmTcA
       for (int q = 0; q < nbq; q++, qg++) {
         mbar_wait_a<true>(bar0 + RAW_FULL + 8 * rs, rpar, limit);
         const uint32_t so = rs * TC_STAGE_BYTES;
+        // d_w * d_x of a block for the warp's 4 tokens (_mm256_mul_ps(d0, d1), ggml.c:1431): block 0 here, blocks 1..3 one
+        // step ahead, under the latency of the previous block's tcgen05.ld
+        float sc[TH];
+        {
+          const float dwb = lds_f32(dw0 + so);
+          const float4 dx4 = lds_f32x4(dx0 + so);
+          sc[0] = __fmul_rn(dwb, dx4.x); sc[1] = __fmul_rn(dwb, dx4.y); sc[2] = __fmul_rn(dwb, dx4.z); sc[3] = __fmul_rn(dwb, dx4.w);
+        }
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-          // d_w * d_x of this block for the warp's 4 tokens, before the accumulators arrive (the scales die here)
-          const float dwb = lds_f32(dw0 + so + 4 * b);
-          const float4 dx4 = lds_f32x4(dx0 + so + b * TC_T * 4);
-          u64 s2[TH];
-          {
-            const float s0 = __fmul_rn(dwb, dx4.x), s1 = __fmul_rn(dwb, dx4.y), s2f = __fmul_rn(dwb, dx4.z), s3 = __fmul_rn(dwb, dx4.w);   // _mm256_mul_ps(d0, d1), ggml.c:1431
-            s2[0] = pack_f2(s0, s0); s2[1] = pack_f2(s1, s1); s2[2] = pack_f2(s2f, s2f); s2[3] = pack_f2(s3, s3);
-          }
           if (threadIdx.x == 0) TC_STAMP(10, qg * 4 + b);
           mbar_wait_a<B200_TC_EPI_SLEEP != 0>(bar0 + TM_FULL + 8 * b, qg & 1, limit);
           if (threadIdx.x == 0) TC_STAMP(7, qg * 4 + b);
           tc_fence_after();
+          float dwn = 0.0f;
+          float4 dxn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #if B200_TC_LD16
-          // two 16-column loads: half the live registers of one 32-column load, which lets the compiler keep the loop's
-          // addresses in registers under the 80-register cap of 704 threads
+          // two 16-column loads: half the live registers of one 32-column load
           uint32_t d[16];
           tmem_ld16(taddr0 + (uint32_t) b * TC_N, d);
+          if (b < 3) { dwn = lds_f32(dw0 + so + 4 * (b + 1)); dxn = lds_f32x4(dx0 + so + (b + 1) * TC_T * 4); }
           tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 2; t++)
+          for (int t = 0; t < 2; t++) {
+            const u64 s2 = pack_f2(sc[t], sc[t]);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-              acc[t][j] = ffma2(s2[t], pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+              acc[t][j] = ffma2(s2, pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+          }
           tmem_ld16(taddr0 + (uint32_t) b * TC_N + 16u, d);
           tmem_ld_wait();
           if (threadIdx.x == 0) TC_STAMP(8, qg * 4 + b);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
+          if (elect_one_sync()) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
 #pragma unroll
-          for (int t = 2; t < 4; t++)
+          for (int t = 2; t < 4; t++) {
+            const u64 s2 = pack_f2(sc[t], sc[t]);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-              acc[t][j] = ffma2(s2[t], pack_i2((int) d[(t - 2) * 8 + 2 * j], (int) d[(t - 2) * 8 + 2 * j + 1]), acc[t][j]);
+              acc[t][j] = ffma2(s2, pack_i2((int) d[(t - 2) * 8 + 2 * j], (int) d[(t - 2) * 8 + 2 * j + 1]), acc[t][j]);
+          }
 #else
           uint32_t d[32];                                  // 32 columns = this warp's 4 tokens x 8 lanes
           tmem_ld32(taddr0 + (uint32_t) b * TC_N, d);
+          if (b < 3) { dwn = lds_f32(dw0 + so + 4 * (b + 1)); dxn = lds_f32x4(dx0 + so + (b + 1) * TC_T * 4); }
           tmem_ld_wait();
           if (threadIdx.x == 0) TC_STAMP(8, qg * 4 + b);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
+          if (elect_one_sync()) mbar_arrive_a(bar0 + TM_EMPTY + 8 * b);      // the accumulator buffer is free as soon as it is in registers
 #pragma unroll
-          for (int t = 0; t < TH; t++)
+          for (int t = 0; t < TH; t++) {
+            const u64 s2 = pack_f2(sc[t], sc[t]);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-              acc[t][j] = ffma2(s2[t], pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+              acc[t][j] = ffma2(s2, pack_i2((int) d[t * 8 + 2 * j], (int) d[t * 8 + 2 * j + 1]), acc[t][j]);   // _mm256_fmadd_ps, ggml.c:1457
+          }
 #endif
+          if (b < 3) { sc[0] = __fmul_rn(dwn, dxn.x); sc[1] = __fmul_rn(dwn, dxn.y); sc[2] = __fmul_rn(dwn, dxn.z); sc[3] = __fmul_rn(dwn, dxn.w); }
         }
         if (threadIdx.x == 0) TC_STAMP(9, qg);
         __syncwarp();
-        if (lane == 0) mbar_arrive_a(bar0 + RAW_EMPTY + 8 * rs);
+        if (elect_one_sync()) mbar_arrive_a(bar0 + RAW_EMPTY + 8 * rs);
         if (++rs == TC_RAW_STAGES) { rs = 0; rpar ^= 1; }
       }
       // horizontal sum exactly as ggml.c:1461-1466: (acc[k] + acc[k+4]) k < 4, then (r0 + r2) + (r1 + r3)
