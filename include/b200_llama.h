@@ -108,6 +108,26 @@ int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const in
 
 uint32_t b200_rng_next_u32(b200_rng *r);
 
+/* The same sampler with its candidate stage on the GPU (utils.cpp:359-386, called at PO.mm:865):
+ * b200_llama_eval_topk == b200_llama_eval followed by the repetition penalty and the top_k selection of
+ * llama_sample_top_p_top_k ON THE DEVICE, so that top_k (value, id) pairs cross PCIe instead of n_vocab logits.
+ * On return *n_cand == top_k and (cand_values, cand_ids) are the reference's logits_id after sample_top_k, in its
+ * order -- or *n_cand == 0 when that order is not determined by the values alone (two of the best top_k + 1 compare
+ * equal, NaN) or the request is outside what the kernel covers (top_k > 64, n_last > 256): the evaluation has still
+ * run, and the caller fetches the logits with b200_llama_last_logits and calls b200_llama_sample_top_p_top_k.
+ * b200_llama_sample_from_candidates == the rest of llama_sample_top_p_top_k (utils.cpp:388-428): soft-max over the
+ * candidates, top_p cut, std::discrete_distribution draw.  cand_values / cand_ids: room for top_k entries. */
+int b200_llama_eval_topk(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens,
+                         const int32_t *last_n_tokens, int n_last, double repeat_penalty, double temp, int top_k,
+                         double *cand_values, int32_t *cand_ids, int *n_cand, char *err, size_t errlen);
+int b200_llama_last_logits(b200_llama *m, float *logits_out, char *err, size_t errlen);
+/* kernel-level entry of the candidate stage on host logits (tests, timing); kernel_ms (optional) = best-of-5 device time */
+int b200_sample_topk(int device, const float *logits, int n_vocab, const int32_t *last_n_tokens, int n_last, double repeat_penalty,
+                     double temp, int top_k, double *cand_values, int32_t *cand_ids, int *n_cand, float *kernel_ms,
+                     char *err, size_t errlen);
+int32_t b200_llama_sample_from_candidates(const double *cand_values, const int32_t *cand_ids, int n_cand, double top_p,
+                                          b200_rng *rng);
+
 /* ---- the token loop itself: -[LlamaPredictOperation main], PO.mm:768-901, as one call ---------------------------------
  * The compiled-code mirror of the reference's host layer (csrc/host_runner.cpp): model load (resident between runs),
  * prompt tokenization with BOS, the 4-token probe evaluation, prompt slices of n_batch + 1 tokens, sampling with the
@@ -135,6 +155,9 @@ int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ct
                         const char *const *pieces, const int *piece_lens, const char *prompt, size_t prompt_len,
                         const char *antiprompt, size_t antiprompt_len, const b200_run_params *params,
                         b200_event_fn on_event, void *user);
+/* How the sampling steps of the calling thread's last b200_llama_run were served: with the candidate stage on the GPU
+ * (b200_llama_eval_topk) or, for an ambiguous candidate order / B200_HOST_SAMPLER=1, by the host sampler on the full logits. */
+void b200_llama_run_sampler_stats(int *gpu_sampled, int *host_sampled);
 
 /* Device-resident decode loop (no reference equivalent; used by bench.py's `value` leg and by teacher-forced
  * parity runs).  Starting with `first_token` at position n_past, runs n_steps single-token evaluations entirely on

@@ -113,6 +113,17 @@ def lib() -> C.CDLL:
         L.b200_rng_free.argtypes, L.b200_rng_free.restype = [vp], None
         L.b200_llama_sample_top_p_top_k.argtypes = [ci, vp, vp, ci, C.c_double, ci, C.c_double, C.c_double, vp]
         L.b200_llama_sample_top_p_top_k.restype = ci
+    if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_eval_topk"):
+        dbl = C.c_double
+        L.b200_llama_eval_topk.argtypes = [vp, ci, ci, vp, ci, vp, ci, dbl, dbl, ci, vp, vp, C.POINTER(ci), cp, sz]
+        L.b200_llama_eval_topk.restype = ci
+        L.b200_llama_last_logits.argtypes, L.b200_llama_last_logits.restype = [vp, vp, cp, sz], ci
+        L.b200_llama_sample_from_candidates.argtypes = [vp, vp, ci, dbl, vp]
+        L.b200_llama_sample_from_candidates.restype = ci
+        L.b200_sample_topk.argtypes = [ci, vp, ci, vp, ci, dbl, dbl, ci, vp, vp, C.POINTER(ci), C.POINTER(C.c_float), cp, sz]
+        L.b200_sample_topk.restype = ci
+        L.b200_llama_run_sampler_stats.argtypes = [C.POINTER(ci), C.POINTER(ci)]
+        L.b200_llama_run_sampler_stats.restype = None
     if "B200_LIB" not in os.environ or hasattr(L, "b200_llama_run"):
         L.b200_run_params_default.argtypes, L.b200_run_params_default.restype = [C.POINTER(RunParams)], None
         L.b200_llama_run.argtypes = [cp, cp, sz, cp, sz, C.POINTER(RunParams), EVENT_FN, vp]
@@ -291,6 +302,52 @@ def llama_eval(model: LlamaModel, n_threads: int, n_past: int, embd_inp) -> np.n
     return logits
 
 
+def llama_eval_topk(model: LlamaModel, n_threads: int, n_past: int, embd_inp, last_n_tokens, repeat_penalty=1.3, top_k=40, temp=0.8):
+    """llama_eval + the candidate stage of llama_sample_top_p_top_k (utils.cpp:359-386) on the GPU: returns (values, ids), the
+    reference's logits_id after sample_top_k -- or None when that order is not determined by the values alone (then
+    llama_last_logits + Sampler.sample give the reference's answer)."""
+    toks = np.ascontiguousarray(embd_inp, dtype=np.int32)
+    last = np.ascontiguousarray(last_n_tokens, dtype=np.int32)
+    vals, ids, n = np.empty(max(1, top_k), np.float64), np.empty(max(1, top_k), np.int32), C.c_int(0)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_eval_topk(model._h, n_threads, n_past, toks.ctypes.data, len(toks), last.ctypes.data, len(last), repeat_penalty,
+                                    temp, top_k, vals.ctypes.data, ids.ctypes.data, C.byref(n), err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return (vals[:n.value], ids[:n.value]) if n.value else None
+
+
+def llama_last_logits(model: LlamaModel) -> np.ndarray:
+    """The logits of the last evaluation, still on the device after llama_eval_topk."""
+    logits = np.empty(model.n_vocab, dtype=np.float32)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_llama_last_logits(model._h, logits.ctypes.data, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    return logits
+
+
+def sample_topk(logits, last_n_tokens, repeat_penalty=1.3, top_k=40, temp=0.8, device: int = 0, timed: bool = False):
+    """Kernel-level entry of the sampler's candidate stage on host logits: (values, ids) or None if ambiguous."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    last = np.ascontiguousarray(last_n_tokens, dtype=np.int32)
+    vals, ids, n, ms = np.empty(max(1, top_k), np.float64), np.empty(max(1, top_k), np.int32), C.c_int(0), C.c_float(0)
+    err = C.create_string_buffer(512)
+    rc = lib().b200_sample_topk(device, lg.ctypes.data, len(lg), last.ctypes.data, len(last), repeat_penalty, temp, top_k,
+                                vals.ctypes.data, ids.ctypes.data, C.byref(n), C.byref(ms) if timed else None, err, 512)
+    if rc != 0:
+        raise LlamaError(rc, err.value.decode(errors="replace"))
+    res = (vals[:n.value], ids[:n.value]) if n.value else None
+    return (res, ms.value) if timed else res
+
+
+def run_sampler_stats():
+    """(sampling steps served with the candidate stage on the GPU, by the host sampler) of this thread's last LlamaRunner.run."""
+    a, b = C.c_int(0), C.c_int(0)
+    lib().b200_llama_run_sampler_stats(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
 def q4_0_matvec(w_blocks: np.ndarray, x: np.ndarray, lane_pairs: int = 0, device: int = 0, timed: bool = False):
     """out[M] = W (Q4_0, ggml rows of 20-byte blocks) * x through the production mat-vec kernel."""
     w = np.ascontiguousarray(w_blocks, dtype=np.uint8)
@@ -382,6 +439,12 @@ class Sampler:
         last = np.ascontiguousarray(last_n_tokens, dtype=np.int32)
         return int(lib().b200_llama_sample_top_p_top_k(len(lg), lg.ctypes.data, last.ctypes.data, len(last),
                                                        repeat_penalty, top_k, top_p, temp, self._h))
+
+    def sample_from_candidates(self, values, ids, top_p=0.95) -> int:
+        """The rest of llama_sample_top_p_top_k (utils.cpp:388-428) on the candidates of llama_eval_topk / sample_topk."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        return int(lib().b200_llama_sample_from_candidates(v.ctypes.data, i.ctypes.data, len(v), top_p, self._h))
 
     def __del__(self):
         try:

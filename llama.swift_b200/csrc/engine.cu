@@ -30,6 +30,7 @@
 #include "megakernel.cuh"
 #include "batch.cuh"
 #include "prefill_tc.cuh"
+#include "sample_topk.cuh"
 
 namespace b200 {
 void host_build_tables(uint16_t *table_silu_f16, uint16_t *table_exp_f16);
@@ -337,6 +338,8 @@ struct b200_llama {
   size_t logits_log_cap = 0;
   int log_cap = 0;
   float *h_logits = nullptr;        // pinned
+  TopkOut *d_topk = nullptr, *h_topk = nullptr;      // GPU candidate stage of the sampler (sample_topk.cuh); h_topk pinned
+  int32_t *d_last_n = nullptr, *h_last_n = nullptr;  // repetition window, h_last_n pinned
   unsigned int *h_abort = nullptr;  // pinned copy of the device abort word (ptx.cuh: bounded waits)
   float kq_scale = 0.f;
   long long weight_bytes = 0;
@@ -652,6 +655,9 @@ void free_model(b200_llama *m) {
   cudaFree(m->out.d_wtc);
   cudaFree(m->d_sp); cudaFree(m->d_token_log); cudaFree(m->d_forced); cudaFree(m->d_logits_log);
   if (m->h_logits) cudaFreeHost(m->h_logits);
+  cudaFree(m->d_topk); cudaFree(m->d_last_n);
+  if (m->h_topk) cudaFreeHost(m->h_topk);
+  if (m->h_last_n) cudaFreeHost(m->h_last_n);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   for (cudaEvent_t e : m->kev) cudaEventDestroy(e);
@@ -1243,10 +1249,39 @@ static int eval_enqueue_token(b200_llama *m, int n_threads, int token, int pos, 
   return B200_LLAMA_OK;
 }
 
-int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits_out,
-                    char *err, size_t errlen) {
+// the candidate stage of the sampler, enqueued behind the evaluation on the leader's stream
+struct TopkReq {
+  const int32_t *last_n;
+  int n_last;
+  double scale, penalty;
+  int top_k;
+};
+
+static cudaError_t enqueue_topk(b200_llama *m, const TopkReq &tk) {
+  cudaError_t e;
+  if (!m->d_topk) {
+    if ((e = cudaMalloc(&m->d_topk, sizeof(TopkOut))) != cudaSuccess) return e;
+    if ((e = cudaMallocHost(&m->h_topk, sizeof(TopkOut))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&m->d_last_n, TOPK_MAX_LAST * 4)) != cudaSuccess) return e;
+    if ((e = cudaMallocHost(&m->h_last_n, TOPK_MAX_LAST * 4)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sample_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) topk_smem_bytes(m->n_vocab))) != cudaSuccess) return e;
+  }
+  if (tk.n_last > 0) {
+    memcpy(m->h_last_n, tk.last_n, (size_t) tk.n_last * 4);
+    if ((e = cudaMemcpyAsync(m->d_last_n, m->h_last_n, (size_t) tk.n_last * 4, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return e;
+  }
+  sample_topk_kernel<<<1, TOPK_THREADS, topk_smem_bytes(m->n_vocab), m->stream>>>(m->d_logits, m->n_vocab, m->d_last_n, tk.n_last, tk.scale,
+                                                                                   tk.penalty, tk.top_k, m->d_topk);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  m->last_launches++;
+  return cudaMemcpyAsync(m->h_topk, m->d_topk, sizeof(TopkOut), cudaMemcpyDeviceToHost, m->stream);
+}
+
+// logits_out == nullptr: the logits stay on the device (tk != nullptr: only the sampler's candidates come back)
+static int eval_core(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits_out,
+                     const TopkReq *tk, char *err, size_t errlen) {
   const int fail_code = B200_LLAMA_ERR_PREDICT;
-  if (!m || !tokens || !logits_out) { set_err(err, errlen, "null argument"); return fail_code; }
+  if (!m || !tokens) { set_err(err, errlen, "null argument"); return fail_code; }
   if (n_tokens < 1 || n_past < 0 || n_past + n_tokens > m->n_ctx) {
     set_err(err, errlen, "n_past %d + n_tokens %d exceeds n_ctx %d", n_past, n_tokens, m->n_ctx);
     return fail_code;
@@ -1269,12 +1304,13 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
       CUDA_TRY(enqueue_batch_chunk(m, n_threads, n_past, n_tokens, t0, n, tokens, t0 + n == n_tokens, &m->last_launches));
     }
     CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_out) CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (tk) CUDA_TRY(enqueue_topk(m, *tk));
     CUDA_TRY(abort_fetch_async(m));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     { float ms = 0; if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_eval_ms = ms; }
     if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the evaluation was abandoned and the exchange state reset"); return fail_code; }
-    memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
+    if (logits_out) memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
     return B200_LLAMA_OK;
   }
   // Token-major enqueue: the token kernels of a group wait for each other ON THE GPUS, so every rank must receive
@@ -1291,7 +1327,8 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
   }
   for (b200_llama *r : ranks) {
     CUDA_TRY(cudaSetDevice(r->device));
-    CUDA_TRY(cudaMemcpyAsync(r->h_logits, r->d_logits, (size_t) r->n_vocab * 4, cudaMemcpyDeviceToHost, r->stream));
+    if (logits_out && r == m) CUDA_TRY(cudaMemcpyAsync(r->h_logits, r->d_logits, (size_t) r->n_vocab * 4, cudaMemcpyDeviceToHost, r->stream));
+    if (tk && r == m) CUDA_TRY(enqueue_topk(m, *tk));
     CUDA_TRY(abort_fetch_async(r));
   }
   for (b200_llama *r : ranks) {
@@ -1299,7 +1336,42 @@ int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tok
     CUDA_TRY(cudaStreamSynchronize(r->stream));
   }
   if (abort_check_and_reset(ranks)) { set_err(err, errlen, "a device-side wait timed out; the evaluation was abandoned and the exchange state reset"); return fail_code; }
-  memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);      // every rank holds the full logits; the leader's are returned
+  if (logits_out) memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);      // every rank holds the full logits; the leader's are returned
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_eval(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits_out,
+                    char *err, size_t errlen) {
+  if (!logits_out) { set_err(err, errlen, "null argument"); return B200_LLAMA_ERR_PREDICT; }
+  return eval_core(m, n_threads, n_past, tokens, n_tokens, logits_out, nullptr, err, errlen);
+}
+
+int b200_llama_eval_topk(b200_llama *m, int n_threads, int n_past, const int32_t *tokens, int n_tokens,
+                         const int32_t *last_n_tokens, int n_last, double repeat_penalty, double temp, int top_k,
+                         double *cand_values, int32_t *cand_ids, int *n_cand, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  if (!m || !cand_values || !cand_ids || !n_cand || (n_last > 0 && !last_n_tokens)) { set_err(err, errlen, "null argument"); return fail_code; }
+  *n_cand = 0;
+  // outside what the kernel covers the evaluation still runs; the caller fetches the logits (b200_llama_last_logits)
+  const bool covered = top_k >= 1 && top_k <= TOPK_MAX_K && n_last >= 0 && n_last <= TOPK_MAX_LAST &&
+                       topk_smem_bytes(m->n_vocab) <= 40 * 1024;
+  TopkReq tk{last_n_tokens, n_last, 1.0 / temp, repeat_penalty, std::min(top_k, m->n_vocab)};   // const double scale = 1.0/temp, utils.cpp:357
+  const int rc = eval_core(m, n_threads, n_past, tokens, n_tokens, nullptr, covered ? &tk : nullptr, err, errlen);
+  if (rc != B200_LLAMA_OK || !covered) return rc;
+  const TopkOut &o = *m->h_topk;
+  if (o.ambiguous || o.n < tk.top_k) return B200_LLAMA_OK;       // equal values among the best: only the reference's own partial_sort knows their order
+  for (int i = 0; i < tk.top_k; i++) { cand_values[i] = o.values[i]; cand_ids[i] = o.ids[i]; }
+  *n_cand = tk.top_k;
+  return B200_LLAMA_OK;
+}
+
+int b200_llama_last_logits(b200_llama *m, float *logits_out, char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  if (!m || !logits_out) { set_err(err, errlen, "null argument"); return fail_code; }
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
   return B200_LLAMA_OK;
 }
 
@@ -1677,6 +1749,56 @@ static int q4_matvec_impl(int qtype, int device, const void *w_ggml, int M, int 
   return rc;
 }
 
+
+/* Kernel-level entry of the sampler's candidate stage (sample_topk.cuh) on host logits: what b200_llama_eval_topk runs behind
+ * the evaluation.  *n_cand = top_k, or 0 when the candidate order is ambiguous (see the header).  kernel_ms: best of 5. */
+int b200_sample_topk(int device, const float *logits, int n_vocab, const int32_t *last_n_tokens, int n_last, double repeat_penalty,
+                     double temp, int top_k, double *cand_values, int32_t *cand_ids, int *n_cand, float *kernel_ms,
+                     char *err, size_t errlen) {
+  const int fail_code = B200_LLAMA_ERR_PREDICT;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { set_err(err, errlen, "no CUDA device available (this library has no CPU path)"); return fail_code; }
+  if (!logits || !cand_values || !cand_ids || !n_cand || n_vocab < 1 || top_k < 1 || top_k > TOPK_MAX_K || n_last < 0 || n_last > TOPK_MAX_LAST ||
+      topk_smem_bytes(n_vocab) > 40 * 1024) { set_err(err, errlen, "bad argument"); return fail_code; }
+  CUDA_TRY(cudaSetDevice(device));
+  float *d_logits = nullptr;
+  int32_t *d_last = nullptr;
+  TopkOut *d_out = nullptr;
+  TopkOut h_out;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() { cudaFree(d_logits); cudaFree(d_last); cudaFree(d_out); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+#define TK_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return fail_code; } } while (0)
+  TK_TRY(cudaMalloc(&d_logits, (size_t) n_vocab * 4));
+  TK_TRY(cudaMalloc(&d_last, TOPK_MAX_LAST * 4));
+  TK_TRY(cudaMalloc(&d_out, sizeof(TopkOut)));
+  TK_TRY(cudaMemcpy(d_logits, logits, (size_t) n_vocab * 4, cudaMemcpyHostToDevice));
+  if (n_last) TK_TRY(cudaMemcpy(d_last, last_n_tokens, (size_t) n_last * 4, cudaMemcpyHostToDevice));
+  TK_TRY(cudaFuncSetAttribute(sample_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) topk_smem_bytes(n_vocab)));
+  TK_TRY(cudaEventCreate(&e0));
+  TK_TRY(cudaEventCreate(&e1));
+  const int k = std::min(top_k, n_vocab);
+  float best = 1e30f;
+  for (int rep = 0; rep < (kernel_ms ? 5 : 1); rep++) {
+    TK_TRY(cudaEventRecord(e0));
+    sample_topk_kernel<<<1, TOPK_THREADS, topk_smem_bytes(n_vocab)>>>(d_logits, n_vocab, d_last, n_last, 1.0 / temp, repeat_penalty, k, d_out);
+    TK_TRY(cudaGetLastError());
+    TK_TRY(cudaEventRecord(e1));
+    TK_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    TK_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  TK_TRY(cudaMemcpy(&h_out, d_out, sizeof(TopkOut), cudaMemcpyDeviceToHost));
+#undef TK_TRY
+  cleanup();
+  if (kernel_ms) *kernel_ms = best;
+  *n_cand = 0;
+  if (!h_out.ambiguous && h_out.n >= k) {
+    for (int i = 0; i < k; i++) { cand_values[i] = h_out.values[i]; cand_ids[i] = h_out.ids[i]; }
+    *n_cand = k;
+  }
+  return B200_LLAMA_OK;
+}
 
 #if B200_TC_TRACE
 /* development build only (-DB200_TC_TRACE=1): the hand-over timeline of CTA 0 of the last tcgen05 mat-mul launch */

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,10 +52,15 @@ void b200_run_params_default(b200_run_params *p) {
   p->device = 0;
 }
 
-int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ctx, const b200_tokenizer *tok,
-                        const char *const *pieces, const int *piece_lens, const char *prompt, size_t prompt_len,
-                        const char *antiprompt, size_t antiprompt_len, const b200_run_params *params,
-                        b200_event_fn on_event, void *user) {
+// gpu_model != nullptr: the evaluation that is followed by a sampling step runs as b200_llama_eval_topk, i.e. the penalty /
+// top_k stage of the sampler happens on the GPU and only top_k (value, id) pairs come back (320 B + ids instead of 128 KB).
+static thread_local int g_gpu_sampled = 0, g_host_sampled = 0;
+
+static int run_loop_impl(b200_eval_fn eval, void *eval_ctx, b200_llama *gpu_model, int n_vocab, int n_ctx, const b200_tokenizer *tok,
+                         const char *const *pieces, const int *piece_lens, const char *prompt, size_t prompt_len,
+                         const char *antiprompt, size_t antiprompt_len, const b200_run_params *params,
+                         b200_event_fn on_event, void *user) {
+  g_gpu_sampled = g_host_sampled = 0;
   if (!eval || !tok || !params || !pieces || !piece_lens || n_vocab < 4 || n_ctx < 4) return B200_LLAMA_ERR_PREDICT;
   const EventSink sink{on_event, user};
   char err[512] = {0};
@@ -89,20 +95,46 @@ int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ct
   int n_past = 0, remaining = n_predict;
   size_t consumed = 0;
 
+  // The reference routes top_k / top_p / temp / repeat_penalty through `const float` locals (PO.mm:852-855) before they widen
+  // to the sampler's int / double parameters.
+  const float top_k = (float) params->top_k, top_p = params->top_p, temp = params->temp, penalty = params->repeat_penalty;
+  std::vector<double> cand_v((size_t) std::max(1, (int) top_k));
+  std::vector<int32_t> cand_i((size_t) std::max(1, (int) top_k));
+
   while (remaining > 0) {                                                                  // PO.mm:834
+    int n_cand = 0;
+    bool logits_on_host = true;
     if (!embd.empty()) {
-      const int rc = eval(eval_ctx, params->n_threads, n_past, embd.data(), (int) embd.size(), logits.data(), err, sizeof err);
+      int rc;
+      if (gpu_model && embd_inp.size() <= consumed) {
+        // this evaluation is followed by a sampling step: candidate stage on the GPU.  last_n already holds embd (pushed when
+        // the tokens were appended), which is the window the sampler will see.
+        rc = b200_llama_eval_topk(gpu_model, params->n_threads, n_past, embd.data(), (int) embd.size(), last_n.data(), (int) last_n.size(),
+                                  (double) penalty, (double) temp, (int) top_k, cand_v.data(), cand_i.data(), &n_cand, err, sizeof err);
+        logits_on_host = false;
+      } else {
+        rc = eval(eval_ctx, params->n_threads, n_past, embd.data(), (int) embd.size(), logits.data(), err, sizeof err);
+      }
       if (rc != B200_LLAMA_OK) { sink.post(B200_EVENT_FAILED, err, (int) strlen(err), B200_LLAMA_ERR_PREDICT); return rc; }
     }
     n_past += (int) embd.size();
     embd.clear();
 
     if (embd_inp.size() <= consumed) {
-      // out of prompt: sample.  The reference routes top_k / top_p / temp / repeat_penalty through `const float`
-      // locals (PO.mm:852-855) before they widen to the sampler's int / double parameters.
-      const float top_k = (float) params->top_k, top_p = params->top_p, temp = params->temp, penalty = params->repeat_penalty;
-      const int32_t id = b200_llama_sample_top_p_top_k(n_vocab, logits.data(), last_n.data(), (int) last_n.size(),
-                                                       (double) penalty, (int) top_k, (double) top_p, (double) temp, rng);
+      // out of prompt: sample
+      int32_t id;
+      if (n_cand > 0) {
+        id = b200_llama_sample_from_candidates(cand_v.data(), cand_i.data(), n_cand, (double) top_p, rng);
+        g_gpu_sampled++;
+      } else {
+        if (!logits_on_host) {    // the values alone do not determine the reference's candidate order: its own library call decides
+          const int rc = b200_llama_last_logits(gpu_model, logits.data(), err, sizeof err);
+          if (rc != B200_LLAMA_OK) { sink.post(B200_EVENT_FAILED, err, (int) strlen(err), B200_LLAMA_ERR_PREDICT); return rc; }
+        }
+        id = b200_llama_sample_top_p_top_k(n_vocab, logits.data(), last_n.data(), (int) last_n.size(),
+                                           (double) penalty, (int) top_k, (double) top_p, (double) temp, rng);
+        g_host_sampled++;
+      }
       if (!last_n.empty()) { last_n.erase(last_n.begin()); last_n.push_back(id); }         // PO.mm:867-868
       embd.push_back(id);
       --remaining;
@@ -122,6 +154,19 @@ int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ct
   }
   sink.post(B200_EVENT_COMPLETED);                                                         // PO.mm:898
   return B200_LLAMA_OK;
+}
+
+int b200_llama_run_loop(b200_eval_fn eval, void *eval_ctx, int n_vocab, int n_ctx, const b200_tokenizer *tok,
+                        const char *const *pieces, const int *piece_lens, const char *prompt, size_t prompt_len,
+                        const char *antiprompt, size_t antiprompt_len, const b200_run_params *params,
+                        b200_event_fn on_event, void *user) {
+  return run_loop_impl(eval, eval_ctx, nullptr, n_vocab, n_ctx, tok, pieces, piece_lens, prompt, prompt_len, antiprompt, antiprompt_len,
+                       params, on_event, user);
+}
+
+void b200_llama_run_sampler_stats(int *gpu_sampled, int *host_sampled) {
+  if (gpu_sampled) *gpu_sampled = g_gpu_sampled;
+  if (host_sampled) *host_sampled = g_host_sampled;
 }
 
 static int eval_on_model(void *ctx, int n_threads, int n_past, const int32_t *tokens, int n_tokens, float *logits, char *err,
@@ -148,8 +193,10 @@ int b200_llama_run(const char *model_path, const char *prompt, size_t prompt_len
   std::vector<int> lens((size_t) n_vocab);
   for (int i = 0; i < n_vocab; i++) pieces[(size_t) i] = b200_llama_token_str(model, i, &lens[(size_t) i]);
   const b200_tokenizer *tok = b200_llama_shared_tokenizer(model);      // built once per resident model, not per run
-  const int out = b200_llama_run_loop(eval_on_model, model, n_vocab, b200_llama_n_ctx(model), tok, pieces.data(), lens.data(), prompt,
-                                      prompt_len, antiprompt, antiprompt_len, params, on_event, user);
+  const char *host_only = getenv("B200_HOST_SAMPLER");                  // A/B switch: the whole sampler on the host, 128 KB of logits per token
+  b200_llama *gpu_model = host_only && host_only[0] == '1' ? nullptr : model;
+  const int out = run_loop_impl(eval_on_model, model, gpu_model, n_vocab, b200_llama_n_ctx(model), tok, pieces.data(), lens.data(), prompt,
+                                prompt_len, antiprompt, antiprompt_len, params, on_event, user);
   b200_llama_release(model);                                                               // was ggml_free(model.ctx), PO.mm:900
   return out;
 }

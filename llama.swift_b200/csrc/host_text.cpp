@@ -115,34 +115,10 @@ void b200_rng_free(b200_rng *r) { delete r; }
 
 uint32_t b200_rng_next_u32(b200_rng *r) { return (uint32_t) r->engine(); }   // one raw draw (gpt_random_prompt, utils.cpp:103)
 
-int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const int32_t *last_n_tokens, int n_last,
-                                      double repeat_penalty, int top_k, double top_p, double temp, b200_rng *rng) {
-  if (!logits || !rng || n_vocab <= 0 || top_k <= 0) return -1;
-  if (top_k > n_vocab) top_k = n_vocab;                       // (the reference would run off the end of its vector)
+}  // extern "C"
 
-  std::vector<uint8_t> recent((size_t) n_vocab, 0);
-  for (int i = 0; i < n_last; i++) {
-    const int32_t id = last_n_tokens[i];
-    if (id >= 0 && id < n_vocab) recent[id] = 1;
-  }
-
-  // scaled, penalised logits in vocabulary order (utils.cpp:359-374: the products are formed left to right in double)
-  std::vector<std::pair<double, int32_t>> cand;
-  cand.reserve((size_t) n_vocab);
-  const double scale = 1.0 / temp;
-  for (int i = 0; i < n_vocab; i++) {
-    const float l = logits[i];
-    double v;
-    if (recent[i]) v = (l < 0.0) ? l * scale * repeat_penalty : l * scale / repeat_penalty;
-    else v = l * scale;
-    cand.emplace_back(v, i);
-  }
-
-  // the k best, in the order the reference's own library call leaves them (ties included): utils.cpp:333-343
-  std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(),
-                    [](const std::pair<double, int32_t> &a, const std::pair<double, int32_t> &b) { return a.first > b.first; });
-  cand.resize((size_t) top_k);
-
+// utils.cpp:388-428: soft-max over the kept candidates, nucleus cut, one draw
+static int32_t draw_from_candidates(std::vector<std::pair<double, int32_t>> &cand, double top_p, b200_rng *rng) {
   double top = -INFINITY;
   for (const auto &c : cand) top = std::max(top, c.first);
   std::vector<double> p;
@@ -171,6 +147,48 @@ int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const in
 
   std::discrete_distribution<> pick(p.begin(), p.end());
   return cand[(size_t) pick(rng->engine)].second;
+}
+
+extern "C" {
+
+int32_t b200_llama_sample_top_p_top_k(int n_vocab, const float *logits, const int32_t *last_n_tokens, int n_last,
+                                      double repeat_penalty, int top_k, double top_p, double temp, b200_rng *rng) {
+  if (!logits || !rng || n_vocab <= 0 || top_k <= 0) return -1;
+  if (top_k > n_vocab) top_k = n_vocab;                       // (the reference would run off the end of its vector)
+
+  std::vector<uint8_t> recent((size_t) n_vocab, 0);
+  for (int i = 0; i < n_last; i++) {
+    const int32_t id = last_n_tokens[i];
+    if (id >= 0 && id < n_vocab) recent[id] = 1;
+  }
+
+  // scaled, penalised logits in vocabulary order (utils.cpp:359-374: the products are formed left to right in double)
+  std::vector<std::pair<double, int32_t>> cand;
+  cand.reserve((size_t) n_vocab);
+  const double scale = 1.0 / temp;
+  for (int i = 0; i < n_vocab; i++) {
+    const float l = logits[i];
+    double v;
+    if (recent[i]) v = (l < 0.0) ? l * scale * repeat_penalty : l * scale / repeat_penalty;
+    else v = l * scale;
+    cand.emplace_back(v, i);
+  }
+
+  // the k best, in the order the reference's own library call leaves them (ties included): utils.cpp:333-343
+  std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(),
+                    [](const std::pair<double, int32_t> &a, const std::pair<double, int32_t> &b) { return a.first > b.first; });
+  cand.resize((size_t) top_k);
+
+  return draw_from_candidates(cand, top_p, rng);
+}
+
+int32_t b200_llama_sample_from_candidates(const double *cand_values, const int32_t *cand_ids, int n_cand, double top_p,
+                                          b200_rng *rng) {
+  if (!cand_values || !cand_ids || !rng || n_cand <= 0) return -1;
+  std::vector<std::pair<double, int32_t>> cand;
+  cand.reserve((size_t) n_cand);
+  for (int i = 0; i < n_cand; i++) cand.emplace_back(cand_values[i], cand_ids[i]);
+  return draw_from_candidates(cand, top_p, rng);
 }
 
 }  // extern "C"

@@ -28,7 +28,18 @@ def test_runner_matches_reference_loop(ref_lib, ref_model, prompt, overrides):
         L.ref_llama_free(h)
     events = []
     got = lsb.LlamaRunner(path).run(prompt, params=p, on_event=lambda kind, piece, code: events.append(kind))
+    on_gpu, on_host = lsb.run_sampler_stats()
+    # the same run with the whole sampler on the host (128 KB of logits per token): same ids
+    os.environ["B200_HOST_SAMPLER"] = "1"
+    try:
+        got_host = lsb.LlamaRunner(path).run(prompt, params=p)
+    finally:
+        del os.environ["B200_HOST_SAMPLER"]
+    assert lsb.run_sampler_stats()[0] == 0
     lsb.llama_model_cache_clear()
+    assert got_host == got
+    assert on_gpu + on_host == p.n_predict and on_gpu >= p.n_predict - 2, (on_gpu, on_host)
+    print(f"[runner] {on_gpu} of {p.n_predict} sampling steps with the candidate stage on the GPU")
     pieces = _pieces()
     assert [i for i, _ in got] == [int(x) for x in want_ids]
     assert [s for _, s in got] == [pieces[i] for i, _ in got]
