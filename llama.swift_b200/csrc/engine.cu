@@ -103,16 +103,18 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
   if (lp == 4) rpt = 1;
   p.rpt = rpt;
   if (qtype == 3) {
-    // Q4_1: one thread per row (the reference dot is a single sequential chain per row); at least 4 compute warps
-    // for the prologue.  Stage = cb blocks x rmax rows x 24 B; smem also holds the dequantized activation (K floats).
+    // Q4_1 (kernels_q4_1.cuh): 16 compute warps = one CHAIN warp per group of 32 rows + TERM warps.  A chunk is cb blocks of
+    // every row; its terms (16 floats per block and row) live in a double-buffered tile of r_pad x (cb * 16 + 4) floats, so
+    // cb is sized for ~512 (row, block) items per chunk.  smem also holds the dequantized activation (K floats).
     p.lp = 4;
-    p.threads = std::max(128, (p.rmax + 31) & ~31) + 32;
-    p.cb = std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 24)));
+    p.threads = 16 * 32 + 32;
+    const int r_pad = (p.rmax + 31) & ~31;
+    p.cb = std::max(1, std::min(p.nb, 512 / r_pad));
     p.stage_bytes = (p.cb * p.rmax * 24 + 127) & ~127;
     const int nch = (p.nb + p.cb - 1) / p.cb;
-    const size_t fx = (size_t) K * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8;
+    const size_t fx = (size_t) K * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8 + (size_t) 2 * r_pad * (p.cb * 16 + 4) * 4 + 4 * 8;
     int S1 = (int) ((kSmemBudget - fx - 256) / (p.stage_bytes + 16));
-    p.S = std::max(1, std::min(S1, nch));
+    p.S = std::max(1, std::min(std::min(S1, nch), 12));
     p.smem = (size_t) p.S * p.stage_bytes + fx + (size_t) 2 * p.S * 8;
     p.bytes = (size_t) p.g_total * 4 * p.nb * 24;
     return p;

@@ -3,10 +3,13 @@
 //
 // The reference dot is ONE sequential f32 chain per output row,
 //     sumf += (d0*q0 + m0)*(d1*q2 + m1) + (d0*q1 + m0)*(d1*q3 + m1)      for every byte of every block, in order,
-// compiled without contraction (ISO C mode) -- so the exact-parity kernel has one thread per row walking its row in
-// order (K/2 dependent adds).  That makes Q4_1 latency-bound by construction; it exists for coverage and parity
-// (BASELINE.json config 5), the throughput path is Q4_0.  Same frame as q4_gemv_kernel: TMA loader warp + mbarrier
-// ring, prologue (LayerNorm) and epilogues shared.
+// compiled without contraction (ISO C mode).  Only the "sumf +=" is a chain: the bracketed TERM of every byte is independent
+// work.  So the kernel splits the two: TERM warps (lane = row, one (row group, block) item at a time) compute the 16 terms of
+// a block -- 13 instructions per byte -- into a double-buffered shared-memory tile, and CHAIN warps (lane = row) add them up
+// in the reference's order, K/2 dependent fadd per row and nothing else on that path.  The floor of a Q4_1 mat-vec is that
+// chain: K/2 x the fadd latency (~4.5 cycles) = 4.8 us for K = 4096, 13 us for K = 11008, whatever the bandwidth.
+// (Round 1 walked the whole row with one thread: 35-82 us per matrix, one busy warp per SM.)
+// Same frame as q4_gemv_kernel: TMA loader warp + mbarrier ring, prologue (LayerNorm) and epilogues shared.
 //
 // Device layout of a Q4_1 matrix (load-time re-layout of ggml's per-row [nb m][nb d][nb*16 B] rows, same 24 B per 32
 // weights): CTA c's rows contiguous; chunk k = [cbk][R][16 B nibbles in ggml order] [cbk][R] f32 m [cbk][R] f32 d.
@@ -32,11 +35,18 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
   float *ys = reinterpret_cast<float *>(smem + (size_t) S * a.stage_bytes);     // [K] dequantized activation d1*q + m1
   float *rowres = ys + K;                                                        // [rmax]
   double *red = reinterpret_cast<double *>(rowres + ((a.rmax + 3) & ~3));        // [32]
-  uint64_t *full = reinterpret_cast<uint64_t *>(red + 32);
+  const int r_pad = (a.rmax + 31) & ~31;                                         // rows incl. the idle lanes of the last row group
+  const int tstride = a.cb * 16 + 4;                                             // floats per row of a term tile; tstride / 4 odd: LDS.128 / STS.128 by 32 rows conflict-free
+  float *terms = reinterpret_cast<float *>(red + 32);                            // [2][r_pad][tstride]
+  uint64_t *full = reinterpret_cast<uint64_t *>(terms + (size_t) 2 * r_pad * tstride);
   uint64_t *empty = full + S;
+  uint64_t *tfull = empty + S, *tempty = tfull + 2;                              // term tiles: term warps <-> chain warps
+  const int n_cw = r_pad >> 5;                                                   // chain warps = row groups
+  const int n_tw = (nt >> 5) - n_cw;                                             // term warps
 
   if (tid == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], nt >> 5); }
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_tw); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], n_tw); mbar_init(&tempty[i], n_cw); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -112,36 +122,75 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
   }
   named_bar_sync(1, nt);
 
-  // ---- row loop: one sequential chain per row, ggml.c:1600-1622 ----
-  const bool active = tid < R;
-  const int r = active ? tid : R - 1;
-  float sumf = 0.0f;
-  for (int k = 0; k < nchunks; k++) {
-    const int s = k % S;
-    mbar_wait(&full[s], (k / S) & 1);
-    const int cbk = min(a.cb, nb - k * a.cb);
-    const uint8_t *st = stages + (size_t) s * a.stage_bytes;
-    const uint4 *nib = reinterpret_cast<const uint4 *>(st) + r;
-    const float *pm = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16) + r;
-    const float *pd = pm + (size_t) cbk * R;
-    const float *yk = ys + (size_t) k * a.cb * 32;
-    for (int bl = 0; bl < cbk; bl++) {
-      const uint4 wv = nib[(size_t) bl * R];
-      const float m0 = pm[bl * R], d0 = pd[bl * R];
-      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const uint32_t by = (ww[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        const float f0 = __fadd_rn(__fmul_rn(d0, (float) (by & 0xfu)), m0);
-        const float f1 = __fadd_rn(__fmul_rn(d0, (float) (by >> 4)), m0);
-        const float f2 = yk[bl * 32 + 2 * j], f3 = yk[bl * 32 + 2 * j + 1];
-        sumf = __fadd_rn(sumf, __fadd_rn(__fmul_rn(f0, f2), __fmul_rn(f1, f3)));
+  // ---- row loop, ggml.c:1600-1622 ----
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < n_cw) {
+    // CHAIN warp: lane = row; sumf += term, byte by byte, block by block -- the reference's own order
+    const int r = warp * 32 + lane;
+    float sumf = 0.0f;
+    const float *trow = terms + (size_t) r * tstride;
+    for (int k = 0; k < nchunks; k++) {
+      const int tb = k & 1;
+      mbar_wait(&tfull[tb], (k >> 1) & 1);
+      const int cbk = min(a.cb, nb - k * a.cb);
+      const float4 *t4 = reinterpret_cast<const float4 *>(trow + (size_t) tb * r_pad * tstride);
+      for (int i = 0; i < cbk * 4; i += 4) {          // 16 terms in flight ahead of the chain
+        const float4 v0 = t4[i], v1 = t4[i + 1], v2 = t4[i + 2], v3 = t4[i + 3];
+        sumf = __fadd_rn(sumf, v0.x); sumf = __fadd_rn(sumf, v0.y); sumf = __fadd_rn(sumf, v0.z); sumf = __fadd_rn(sumf, v0.w);
+        sumf = __fadd_rn(sumf, v1.x); sumf = __fadd_rn(sumf, v1.y); sumf = __fadd_rn(sumf, v1.z); sumf = __fadd_rn(sumf, v1.w);
+        sumf = __fadd_rn(sumf, v2.x); sumf = __fadd_rn(sumf, v2.y); sumf = __fadd_rn(sumf, v2.z); sumf = __fadd_rn(sumf, v2.w);
+        sumf = __fadd_rn(sumf, v3.x); sumf = __fadd_rn(sumf, v3.y); sumf = __fadd_rn(sumf, v3.z); sumf = __fadd_rn(sumf, v3.w);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[tb]);
     }
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    if (r < R) rowres[r] = sumf;
+  } else {
+    // TERM warp: items (row group, block) of the chunk, lane = row of the group
+    const int tw = warp - n_cw;
+    for (int k = 0; k < nchunks; k++) {
+      const int s = k % S, tb = k & 1;
+      mbar_wait(&full[s], (k / S) & 1);
+      if (k >= 2) mbar_wait(&tempty[tb], ((k >> 1) - 1) & 1);
+      const int cbk = min(a.cb, nb - k * a.cb);
+      const uint8_t *st = stages + (size_t) s * a.stage_bytes;
+      const float *yk = ys + (size_t) k * a.cb * 32;
+      float *tt = terms + (size_t) tb * r_pad * tstride;
+      for (int it = tw; it < n_cw * cbk; it += n_tw) {
+        const int rg = it / cbk, bl = it - rg * cbk;
+        const int r = rg * 32 + lane;
+        const int rr = r < R ? r : R - 1;              // idle lanes of the last group recompute its last row (never read)
+        const uint4 wv = reinterpret_cast<const uint4 *>(st)[(size_t) bl * R + rr];
+        const float m0 = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16)[bl * R + rr];
+        const float d0 = reinterpret_cast<const float *>(st + (size_t) cbk * R * 20)[bl * R + rr];
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        const float4 *y4 = reinterpret_cast<const float4 *>(yk + bl * 32);
+        float4 *dst = reinterpret_cast<float4 *>(tt + (size_t) r * tstride + bl * 16);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float t[4];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const float4 y = y4[c * 2 + h];            // activation factors d1*q + m1 of 2 bytes (same address for the whole warp)
+            const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int j = h * 2 + e;                 // byte j of word c
+              // (float) nibble without the conversion unit: 0x4B000000 | q is 8388608 + q
+              const float q0 = __fsub_rn(__uint_as_float(((ww[c] >> (8 * j)) & 0xfu) | 0x4B000000u), 8388608.0f);
+              const float q1 = __fsub_rn(__uint_as_float(((ww[c] >> (8 * j + 4)) & 0xfu) | 0x4B000000u), 8388608.0f);
+              const float f0 = __fadd_rn(__fmul_rn(d0, q0), m0);
+              const float f1 = __fadd_rn(__fmul_rn(d0, q1), m0);
+              t[j] = __fadd_rn(__fmul_rn(f0, yy[2 * e]), __fmul_rn(f1, yy[2 * e + 1]));
+            }
+          }
+          dst[c] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&empty[s]); mbar_arrive(&tfull[tb]); }
+    }
   }
-  if (active) rowres[r] = sumf;
   named_bar_sync(1, nt);
   gemv_epilogue<EPI>(a, rp, rowres, tid, nt);
 }
