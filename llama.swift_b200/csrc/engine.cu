@@ -109,10 +109,15 @@ GemvPlan make_plan(int M, int K, int n_sm, int lp_override, int qtype = 2) {
     p.lp = 4;
     p.threads = 16 * 32 + 32;
     const int r_pad = (p.rmax + 31) & ~31;
-    p.cb = std::max(1, std::min(p.nb, 512 / r_pad));
+    const bool terms = q41_term_mode(p.rmax);      // few rows per CTA: term / chain split; many: one thread per row
+    const size_t ys_etc = (size_t) K * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8 + 4 * 8;
+    auto tile_bytes = [&](int cb) { return terms ? (size_t) 2 * r_pad * (cb * 16 + 4) * 4 : (size_t) 0; };
+    p.cb = terms ? std::max(1, std::min(p.nb, 1024 / r_pad)) : std::max(1, std::min(p.nb, stage_bytes_cfg() / (p.rmax * 24)));
+    // at least 3 weight stages next to the activation and the term tiles
+    while (p.cb > 1 && ys_etc + tile_bytes(p.cb) + (size_t) 3 * (((size_t) p.cb * p.rmax * 24 + 127) & ~(size_t) 127) + 512 > kSmemBudget) p.cb--;
     p.stage_bytes = (p.cb * p.rmax * 24 + 127) & ~127;
     const int nch = (p.nb + p.cb - 1) / p.cb;
-    const size_t fx = (size_t) K * 4 + (size_t) ((p.rmax + 3) & ~3) * 4 + 32 * 8 + (size_t) 2 * r_pad * (p.cb * 16 + 4) * 4 + 4 * 8;
+    const size_t fx = ys_etc + tile_bytes(p.cb);
     int S1 = (int) ((kSmemBudget - fx - 256) / (p.stage_bytes + 16));
     p.S = std::max(1, std::min(std::min(S1, nch), 12));
     p.smem = (size_t) p.S * p.stage_bytes + fx + (size_t) 2 * p.S * 8;

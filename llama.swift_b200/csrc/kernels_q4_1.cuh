@@ -18,6 +18,16 @@
 
 namespace b200 {
 
+#ifndef B200_Q41_F32X2
+#define B200_Q41_F32X2 0       // 1 = term warps with packed mul.rn.f32x2 / add.rn.f32x2 (9 instead of 13 instructions per byte): 4 % faster but NOT
+                               // bit-identical to the oracle on B200 (tests/test_gpu_parity.py -k q4_1 fails), so off
+#endif
+
+// Few rows per CTA (wo, w2: 28): term / chain split.  Many rows per CTA (fused wq|wk|wv 84, w1|w3 152, output 220): there are
+// enough rows to fill the SM with one thread per row, and the split's per-chunk hand-overs cost more than they hide (measured:
+// 32000 x 4096 52 us per-row vs 94 us split; 4096 x 11008 82 us per-row vs 43 us split).
+__host__ __device__ __forceinline__ bool q41_term_mode(int rmax) { return ((rmax + 31) & ~31) <= 64; }
+
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_q41[];
@@ -37,12 +47,13 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
   double *red = reinterpret_cast<double *>(rowres + ((a.rmax + 3) & ~3));        // [32]
   const int r_pad = (a.rmax + 31) & ~31;                                         // rows incl. the idle lanes of the last row group
   const int tstride = a.cb * 16 + 4;                                             // floats per row of a term tile; tstride / 4 odd: LDS.128 / STS.128 by 32 rows conflict-free
-  float *terms = reinterpret_cast<float *>(red + 32);                            // [2][r_pad][tstride]
-  uint64_t *full = reinterpret_cast<uint64_t *>(terms + (size_t) 2 * r_pad * tstride);
+  const bool term_mode = q41_term_mode(a.rmax);
+  float *terms = reinterpret_cast<float *>(red + 32);                            // [2][r_pad][tstride] (term mode only)
+  uint64_t *full = reinterpret_cast<uint64_t *>(terms + (term_mode ? (size_t) 2 * r_pad * tstride : (size_t) 0));
   uint64_t *empty = full + S;
   uint64_t *tfull = empty + S, *tempty = tfull + 2;                              // term tiles: term warps <-> chain warps
-  const int n_cw = r_pad >> 5;                                                   // chain warps = row groups
-  const int n_tw = (nt >> 5) - n_cw;                                             // term warps
+  const int n_cw = r_pad >> 5;                                                   // chain warps = row groups (per-row mode: the only busy warps)
+  const int n_tw = term_mode ? (nt >> 5) - n_cw : n_cw;                          // warps that read the weight stages
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_tw); }
@@ -124,7 +135,40 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
 
   // ---- row loop, ggml.c:1600-1622 ----
   const int warp = tid >> 5, lane = tid & 31;
-  if (warp < n_cw) {
+  if (!term_mode) {
+    // one thread per row walks its row in order
+    if (warp < n_cw) {
+      const bool active = tid < R;
+      const int r = active ? tid : R - 1;
+      float sumf = 0.0f;
+      for (int k = 0; k < nchunks; k++) {
+        const int s = k % S;
+        mbar_wait(&full[s], (k / S) & 1);
+        const int cbk = min(a.cb, nb - k * a.cb);
+        const uint8_t *st = stages + (size_t) s * a.stage_bytes;
+        const uint4 *nib = reinterpret_cast<const uint4 *>(st) + r;
+        const float *pm = reinterpret_cast<const float *>(st + (size_t) cbk * R * 16) + r;
+        const float *pd = pm + (size_t) cbk * R;
+        const float *yk = ys + (size_t) k * a.cb * 32;
+        for (int bl = 0; bl < cbk; bl++) {
+          const uint4 wv = nib[(size_t) bl * R];
+          const float m0 = pm[bl * R], d0 = pd[bl * R];
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const uint32_t by = (ww[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const float f0 = __fadd_rn(__fmul_rn(d0, (float) (by & 0xfu)), m0);
+            const float f1 = __fadd_rn(__fmul_rn(d0, (float) (by >> 4)), m0);
+            const float f2 = yk[bl * 32 + 2 * j], f3 = yk[bl * 32 + 2 * j + 1];
+            sumf = __fadd_rn(sumf, __fadd_rn(__fmul_rn(f0, f2), __fmul_rn(f1, f3)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      if (active) rowres[r] = sumf;
+    }
+  } else if (warp < n_cw) {
     // CHAIN warp: lane = row; sumf += term, byte by byte, block by block -- the reference's own order
     const int r = warp * 32 + lane;
     float sumf = 0.0f;
@@ -166,6 +210,32 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
         const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
         const float4 *y4 = reinterpret_cast<const float4 *>(yk + bl * 32);
         float4 *dst = reinterpret_cast<float4 *>(tt + (size_t) r * tstride + bl * 16);
+#if B200_Q41_F32X2
+        const u64 d2 = pack_f2(d0, d0), m2 = pack_f2(m0, m0), magic = pack_f2(8388608.0f, 8388608.0f);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float t[4];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const float4 y = y4[c * 2 + h];            // activation factors d1*q + m1 of 2 bytes (same address for the whole warp)
+            const u64 yy[2] = {pack_f2(y.x, y.y), pack_f2(y.z, y.w)};
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int j = h * 2 + e;                 // byte j of word c
+              // (float) of both nibbles without the conversion unit (0x4B000000 | q is 8388608 + q), then the reference's
+              // (d0*q + m0) * y per nibble as packed multiplies / adds, and the sum of the two products
+              const u64 qb = pack_i2((int) (((ww[c] >> (8 * j)) & 0xfu) | 0x4B000000u), (int) (((ww[c] >> (8 * j + 4)) & 0xfu) | 0x4B000000u));
+              const u64 q2 = fadd2(qb, pack_f2(-8388608.0f, -8388608.0f));
+              const u64 f2 = fadd2(fmul2(d2, q2), m2);
+              float p0, p1;
+              unpack_f2(fmul2(f2, yy[e]), p0, p1);
+              t[j] = __fadd_rn(p0, p1);
+            }
+          }
+          dst[c] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        (void) magic;
+#else
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           float t[4];
@@ -186,6 +256,7 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
           }
           dst[c] = make_float4(t[0], t[1], t[2], t[3]);
         }
+#endif
       }
       __syncwarp();
       if (lane == 0) { mbar_arrive(&empty[s]); mbar_arrive(&tfull[tb]); }

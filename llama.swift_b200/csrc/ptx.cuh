@@ -21,6 +21,13 @@ __device__ __forceinline__ void unpack_f2(u64 v, float &lo, float &hi) {
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
   u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
+// two IEEE fp32 multiplies / adds in one instruction (SASS FMUL2 / FADD2) -- each half rounds like __fmul_rn / __fadd_rn
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 // unsigned bytes (a) x signed bytes (b) + c  (SASS IDP.4A.U8.S8)
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
