@@ -331,8 +331,9 @@ def bench_prefill(args, steps, warmup):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "q4_gemm_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
-                         "note": "algorithmic flops = 2 x 6.607e9 per token + causal attention; the exact per-lane fp32 fma chain of Q4_0 x Q4_0 is drained from TMEM "
-                                 "after every 32-element block, which bounds the kernel (DESIGN.md section 4.4), not the tensor pipe",
+                         "note": "algorithmic flops = 2 x 6.607e9 per token + causal attention; the exact per-lane fp32 fma chain of Q4_0 x Q4_0 needs the "
+                                 "accumulators out of TMEM after every 32-element block, and what the SM must issue for that drain and for the nibble unpack "
+                                 "bounds the kernel (DESIGN.md section 4.4), not the tensor pipe",
                          "ncu": tc_prof},
             "cpu_baseline": None if parity is None else {"value": parity["reference_cpu_tokens_per_s"], "unit": "tokens/s", "cores": args.threads, "kind": "reference",
                                                           "sample": "reference llama_eval of the first 64 prompt tokens in one call (N = 64), %d threads" % args.threads},
