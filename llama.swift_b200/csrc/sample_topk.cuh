@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) sample_topk_kernel(const float *
     if ((recent[i >> 5] >> (i & 31)) & 1u) key = 0;
     best = max(best, key);
   }
-  if (nan_seen) s_amb = 1;                 // a NaN logit anywhere: the host path decides
+  // A NaN logit anywhere: the host path decides.  This flag is needed, not belt and braces: measured on B200, a NaN never
+  // makes it into the candidate list below although its key is the largest (+Inf and 3e38 do) -- the compiled
+  // "key >= threshold" behaves like the float comparison it is equivalent to for every non-NaN value.
+  if (nan_seen) s_amb = 1;
   {
     const int have = __syncthreads_count(best != 0);                   // threads that own a selectable logit
     if (tid == 0) { s_want = (uint32_t) min(top_k + 1, have); s_prefix = 0; }

@@ -155,3 +155,28 @@ def test_tokenizer_random_vocabularies():
         assert list(tok(t, bos=bos)) == _tokenize_restated(pieces, t, bos)
 
     check()
+
+
+def test_sample_from_candidates_matches_full_sampler():
+    """b200_llama_sample_from_candidates (the tail of llama_sample_top_p_top_k, utils.cpp:388-428) on the candidate list the GPU
+    stage would return -- here formed on the host, utils.cpp:357-386 in numpy doubles -- draws the same ids as the full sampler."""
+    n = 2000
+    rng = np.random.default_rng(9)
+    for p in (dict(), dict(top_k=1), dict(top_p=1.0), dict(temp=0.3, repeat_penalty=1.0), dict(top_k=64, top_p=0.5)):
+        q = dict(repeat_penalty=1.3, top_k=40, top_p=0.95, temp=0.8)
+        q.update(p)
+        full, tail = lsb.Sampler(5), lsb.Sampler(5)
+        last = np.zeros(64, np.int32)
+        for step in range(40):
+            logits = (rng.standard_normal(n) * 3.0).astype(np.float32)
+            want = full.sample(logits, last, **q)
+            v = logits.astype(np.float64) * (1.0 / q["temp"])
+            ids = np.unique(last)
+            v[ids] = np.where(logits[ids] < 0, logits[ids].astype(np.float64) * (1.0 / q["temp"]) * q["repeat_penalty"],
+                              logits[ids].astype(np.float64) * (1.0 / q["temp"]) / q["repeat_penalty"])
+            order = np.argsort(-v, kind="stable")[:q["top_k"]]
+            assert len(np.unique(v[order])) == len(order)           # distinct values: the order is determined by the values alone
+            got = tail.sample_from_candidates(v[order], order.astype(np.int32), q["top_p"])
+            assert got == want, (p, step)
+            last = np.roll(last, -1)
+            last[-1] = want
