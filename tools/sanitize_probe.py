@@ -20,4 +20,19 @@ d = lsb.llama_eval(m, 8, 0, toks[:3])
 t, _, _ = m.decode_device(9, int(ref.argmax()), 4, n_threads=8)
 same = lambda x, y: np.array_equal(x.view(np.uint32), y.view(np.uint32))
 print("sanitize probe:", same(ref, a), same(ref, b), same(c, d), t.tolist())
+# round 2 additions: the tensor-core mat-mul on a 9-token batch, the sampler's candidate stage behind an evaluation and alone,
+# the Q4_1 mat-vec in both of its modes (term / chain split: 28 rows per CTA; one thread per row: 84 rows per CTA)
+m.set_option("batch", 1); m.set_option("tc", 1); m.set_option("tc_min_n", 2)
+e = lsb.llama_eval(m, 8, 0, toks)
+last = np.zeros(64, np.int32)
+cand = lsb.llama_eval_topk(m, 8, 9, toks[:1], last)
+rng = np.random.default_rng(0)
+lg = (rng.standard_normal(32000) * 4).astype(np.float32)
+cand2 = lsb.sample_topk(lg, last)
+ok41 = []
+for M, K in ((4096, 128), (12288, 128)):
+    w = gf.quantize_q4_1((rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32))
+    x = rng.standard_normal(K).astype(np.float32)
+    ok41.append(bool(np.isfinite(lsb.q4_1_matvec(w, x)).all()))
+print("sanitize probe 2:", same(ref, e), cand is not None, cand2 is not None, ok41)
 m.free()
