@@ -55,6 +55,32 @@ def test_tp_group_single_process(oracle_lib, small_model, tp):
         grp.free()
 
 
+def test_tp_group_long_enqueue(small_model):
+    """One host thread, many steps: 600 device-resident steps and a 600-token llama_eval on a single-process group of 2.  Every
+    rank's token kernel waits for its peers ON THE GPU, so the host must hand token i to every rank before it queues enough
+    work on one rank to block in a launch (the driver's pending-launch queue holds ~1K entries) -- the enqueue is token-major
+    with a synchronisation every 64 tokens (engine.cu).  Results must equal the single GPU's."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    n_ctx = 640
+    one = lsb.llama_model_load(small_model, n_ctx=n_ctx, device=0)
+    grp = lsb.llama_model_load_group(small_model, n_ctx=n_ctx, devices=(0, 1))
+    try:
+        rng = np.random.default_rng(17)
+        stream = rng.integers(3, 512, size=601).astype(np.int32)
+        t1, _, _ = one.decode_device(0, int(stream[0]), 600, n_threads=8, forced_tokens=stream[1:])
+        t2, _, ms = grp.decode_device(0, int(stream[0]), 600, n_threads=8, forced_tokens=stream[1:])
+        assert np.array_equal(t1, t2)
+        one.set_option("batch", 0)                  # the group evaluates token by token; compare like with like
+        a = lsb.llama_eval(one, 8, 0, stream[:600])
+        g = lsb.llama_eval(grp, 8, 0, stream[:600])
+        assert np.array_equal(bits(g), bits(a))
+        print(f"[tp] group of 2, single process: 600 device-resident steps ({ms:.1f} ms) and a 600-token llama_eval identical to 1 GPU")
+    finally:
+        one.free()
+        grp.free()
+
+
 @pytest.mark.parametrize("tp", [2, 4, 8])
 def test_tp_group_13b_shapes(oracle_lib, tp):
     """BASELINE.json configs[3]: LLaMA-13B geometry (two-part file, 40 heads, n_ff 13824) row-sharded over the group."""
