@@ -20,7 +20,9 @@ namespace b200 {
 
 #ifndef B200_Q41_F32X2
 #define B200_Q41_F32X2 0       // 1 = term warps with packed mul.rn.f32x2 / add.rn.f32x2 (9 instead of 13 instructions per byte): 4 % faster but NOT
-                               // bit-identical to the oracle on B200 (tests/test_gpu_parity.py -k q4_1 fails), so off
+                               // bit-identical to the oracle (tests/test_gpu_parity.py -k q4_1 fails): ptxas 12.9 CONTRACTS the packed pair
+                               // mul.rn.f32x2 -> add.rn.f32x2 into one FFMA2 (SASS: FFMA2 R, d0, q, m0) although both carry .rn and the build
+                               // uses -fmad=false -- the scalar mul.rn.f32 / add.rn.f32 pair is left alone.  So off.
 #endif
 
 // Few rows per CTA (wo, w2: 28): term / chain split.  Many rows per CTA (fused wq|wk|wv 84, w1|w3 152, output 220): there are

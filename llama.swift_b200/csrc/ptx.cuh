@@ -21,7 +21,9 @@ __device__ __forceinline__ void unpack_f2(u64 v, float &lo, float &hi) {
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
   u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
-// two IEEE fp32 multiplies / adds in one instruction (SASS FMUL2 / FADD2) -- each half rounds like __fmul_rn / __fadd_rn
+// two IEEE fp32 multiplies / adds in one instruction (SASS FMUL2 / FADD2) -- each half rounds like __fmul_rn / __fadd_rn.
+// CAUTION (measured, ptxas 12.9): fadd2(fmul2(a, b), c) is CONTRACTED into one FFMA2 despite the .rn modifiers and -fmad=false;
+// do not feed a packed product straight into a packed add where the reference rounds twice (kernels_q4_1.cuh).
 __device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
   u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
