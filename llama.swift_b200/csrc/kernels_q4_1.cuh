@@ -22,7 +22,8 @@ namespace b200 {
 #define B200_Q41_F32X2 0       // 1 = term warps with packed mul.rn.f32x2 / add.rn.f32x2 (9 instead of 13 instructions per byte): 4 % faster but NOT
                                // bit-identical to the oracle (tests/test_gpu_parity.py -k q4_1 fails): ptxas 12.9 CONTRACTS the packed pair
                                // mul.rn.f32x2 -> add.rn.f32x2 into one FFMA2 (SASS: FFMA2 R, d0, q, m0) although both carry .rn and the build
-                               // uses -fmad=false -- the scalar mul.rn.f32 / add.rn.f32 pair is left alone.  So off.
+                               // uses -fmad=false -- the scalar mul.rn.f32 / add.rn.f32 pair is left alone.  2 = the same with the "+ m0" as two scalar
+                               // adds: bit-identical again, and no faster than the scalar form (20.5 vs 19.9 us, 38.7 vs 40.9 us).  So 0.
 #endif
 
 // Few rows per CTA (wo, w2: 28): term / chain split.  Many rows per CTA (fused wq|wk|wv 84, w1|w3 152, output 220): there are
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
         const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
         const float4 *y4 = reinterpret_cast<const float4 *>(yk + bl * 32);
         float4 *dst = reinterpret_cast<float4 *>(tt + (size_t) r * tstride + bl * 16);
-#if B200_Q41_F32X2
+#if B200_Q41_F32X2 != 0
         const u64 d2 = pack_f2(d0, d0), m2 = pack_f2(m0, m0), magic = pack_f2(8388608.0f, 8388608.0f);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -228,7 +229,14 @@ __global__ void __launch_bounds__(544, 1) q4_1_gemv_kernel(const GemvArgs a) {
               // (d0*q + m0) * y per nibble as packed multiplies / adds, and the sum of the two products
               const u64 qb = pack_i2((int) (((ww[c] >> (8 * j)) & 0xfu) | 0x4B000000u), (int) (((ww[c] >> (8 * j + 4)) & 0xfu) | 0x4B000000u));
               const u64 q2 = fadd2(qb, pack_f2(-8388608.0f, -8388608.0f));
+#if B200_Q41_F32X2 == 2
+              // the "+ m0" as two scalar adds: a packed add behind the packed multiply gets contracted into one FFMA2 by ptxas
+              float g0, g1;
+              unpack_f2(fmul2(d2, q2), g0, g1);
+              const u64 f2 = pack_f2(__fadd_rn(g0, m0), __fadd_rn(g1, m0));
+#else
               const u64 f2 = fadd2(fmul2(d2, q2), m2);
+#endif
               float p0, p1;
               unpack_f2(fmul2(f2, yy[e]), p0, p1);
               t[j] = __fadd_rn(p0, p1);
